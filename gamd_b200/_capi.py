@@ -1,0 +1,247 @@
+"""ctypes binding of ``libgamd_b200.so`` (the C ABI in ``include/gamd_b200.h``).
+
+There is no CPU fallback: if the library cannot be loaded or no CUDA device is usable the
+functions raise ``GamdError``.  Torch is used only to hold device memory and streams; every
+argument crosses the boundary as a raw pointer.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libgamd_b200.so")
+
+OK, EINVAL, ECUDA, EUNSUPPORTED, ECAPACITY, ESTATE, ENOGPU = 0, -1, -2, -3, -4, -5, -6
+NBR_LT, NBR_LE, NBR_SELF, NBR_NOWRAP = 0, 1, 2, 4
+MODEL_LJ, MODEL_WATER, MODEL_DYNBOX = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+_ERR_NAMES = {EINVAL: "EINVAL", ECUDA: "ECUDA", EUNSUPPORTED: "EUNSUPPORTED", ECAPACITY: "ECAPACITY",
+              ESTATE: "ESTATE", ENOGPU: "ENOGPU"}
+
+
+class GamdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gamd_b200 error {_ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("kind", c_int32), ("encoding_size", c_int32), ("hidden_dim", c_int32), ("edge_dim", c_int32),
+                ("conv_layer", c_int32), ("in_feats", c_int32), ("use_bond", c_int32), ("expand_edge", c_int32),
+                ("precision", c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/gamd_b200.h declares
+SIGNATURES = {
+    "gamd_create": (c_int32, [c_int32, POINTER(ModelDesc), POINTER(c_void_p)]),
+    "gamd_destroy": (c_int32, [c_void_p]),
+    "gamd_last_error": (c_char_p, [c_void_p]),
+    "gamd_version": (c_char_p, []),
+    "gamd_reserve": (c_int32, [c_void_p, c_int64, c_int64]),
+    "gamd_load_weight": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "gamd_set_scaler": (c_int32, [c_void_p, c_double, c_double]),
+    "gamd_set_bonds": (c_int32, [c_void_p, c_void_p, c_int64, c_int64]),
+    "gamd_finalize_weights": (c_int32, [c_void_p]),
+    "gamd_neighbor_build": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(c_double), c_float, c_int32, c_void_p]),
+    "gamd_neighbor_count_host": (c_int32, [c_void_p, POINTER(c_int64), c_void_p]),
+    "gamd_neighbor_export": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gamd_model_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(c_double), c_void_p, c_void_p,
+                                     c_int64, c_void_p, c_void_p, c_void_p]),
+    "gamd_compute_forces": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(c_double), c_float, c_void_p,
+                                      c_void_p, c_void_p]),
+    "gamd_compute_forces_host": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(c_double), c_float,
+                                           c_void_p, c_void_p]),
+    "gamd_vv_first_half": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p]),
+    "gamd_vv_second_half": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p]),
+    "gamd_md_run": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, POINTER(c_double),
+                              c_float, c_void_p, c_double, c_int32, c_void_p, c_void_p]),
+    "gamd_md_step_host": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                    POINTER(c_double), c_float, c_void_p, c_double]),
+    "gamd_check_async_errors": (c_int32, [c_void_p, c_void_p]),
+    "gamd_debug_ptr": (c_int32, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
+    "gamd_launch_count": (c_int64, [c_void_p]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load the shared library and bind every symbol; raises GamdError when it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise GamdError(ENOGPU, f"{p} not found - build it with `python -m gamd_b200.build` "
+                                "(nvcc, sm_100a); there is no CPU fallback")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the header and the library diverge
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _box3(box):
+    b = np.broadcast_to(np.asarray(box, dtype=np.float64).reshape(-1), (3,)) if np.ndim(box) else \
+        np.full(3, float(box))
+    return (c_double * 3)(*[float(x) for x in b])
+
+
+def _ptr(t):
+    """raw pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Context:
+    """One model instance on one device (wraps ``gamd_ctx*``)."""
+
+    def __init__(self, kind=MODEL_LJ, encoding_size=128, hidden_dim=128, edge_dim=128, conv_layer=4,
+                 in_feats=0, use_bond=False, expand_edge=True, precision=PREC_FP32, device=0):
+        self.lib = load_library()
+        self.desc = ModelDesc(kind, encoding_size, hidden_dim, edge_dim, conv_layer, in_feats, int(use_bond),
+                              int(expand_edge), precision)
+        self._h = c_void_p()
+        rc = self.lib.gamd_create(device, ctypes.byref(self.desc), ctypes.byref(self._h))
+        if rc:
+            raise GamdError(rc, self.lib.gamd_last_error(None).decode())
+        self.device = device
+        self.cap_atoms = 0
+        self.cap_edges = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.gamd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise GamdError(rc, self.lib.gamd_last_error(self._h).decode())
+
+    # ---- setup ----
+    def reserve(self, max_atoms, max_edges):
+        self._check(self.lib.gamd_reserve(self._h, int(max_atoms), int(max_edges)))
+        self.cap_atoms = max(self.cap_atoms, int(max_atoms))
+        self.cap_edges = max(self.cap_edges, int(max_edges))
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            a = np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
+            self._check(self.lib.gamd_load_weight(self._h, k.encode(), a.ctypes.data, a.size))
+
+    def set_scaler(self, mean, var):
+        self._check(self.lib.gamd_set_scaler(self._h, float(np.asarray(mean).reshape(-1)[0]),
+                                             float(np.asarray(var).reshape(-1)[0])))
+
+    def set_bonds(self, bonds, n_atoms_per_frame):
+        b = np.ascontiguousarray(np.asarray(bonds), dtype=np.int64).reshape(-1, 2)
+        self._check(self.lib.gamd_set_bonds(self._h, b.ctypes.data, b.shape[0], int(n_atoms_per_frame)))
+
+    def finalize(self):
+        self._check(self.lib.gamd_finalize_weights(self._h))
+
+    # ---- stages (torch CUDA tensors in, raw pointers across) ----
+    def neighbor_build(self, pos_f32, box, cutoff, flags=NBR_LT | NBR_SELF, n_frames=1):
+        n = pos_f32.shape[0]
+        self._check(self.lib.gamd_neighbor_build(self._h, _ptr(pos_f32), n, n_frames, _box3(box), float(cutoff),
+                                                 int(flags), _stream()))
+
+    def neighbor_count(self):
+        ne = c_int64()
+        self._check(self.lib.gamd_neighbor_count_host(self._h, ctypes.byref(ne), _stream()))
+        return ne.value
+
+    def neighbor_export(self, want_dist=False):
+        import torch
+        ne = self.neighbor_count()
+        dev = torch.device("cuda", self.device)
+        edge = torch.empty((2, max(ne, 1)), dtype=torch.int64, device=dev)
+        dist = torch.empty((max(ne, 1), 3), dtype=torch.float32, device=dev) if want_dist else None
+        norm = torch.empty((max(ne, 1),), dtype=torch.float32, device=dev) if want_dist else None
+        self._check(self.lib.gamd_neighbor_export(self._h, _ptr(edge), edge.shape[1], _ptr(dist), _ptr(norm), _stream()))
+        if want_dist:
+            return edge[:, :ne], dist[:ne], norm[:ne]
+        return edge[:, :ne]
+
+    def model_forward(self, pos_f32, center, neigh, box, feat=None, n_frames=1):
+        import torch
+        n = pos_f32.shape[0]
+        out = torch.empty((n, 3), dtype=torch.float32, device=pos_f32.device)
+        self._check(self.lib.gamd_model_forward(self._h, _ptr(pos_f32), n, n_frames, _box3(box), _ptr(center),
+                                                _ptr(neigh), int(center.shape[0]), _ptr(feat), _ptr(out), _stream()))
+        return out
+
+    def compute_forces(self, pos_f64, box, cutoff, feat=None, n_frames=1, out=None):
+        import torch
+        n = pos_f64.shape[0]
+        if out is None:
+            out = torch.empty((n, 3), dtype=torch.float64, device=pos_f64.device)
+        self._check(self.lib.gamd_compute_forces(self._h, _ptr(pos_f64), n, n_frames, _box3(box), float(cutoff),
+                                                 _ptr(feat), _ptr(out), _stream()))
+        return out
+
+    def compute_forces_host(self, pos_f64_np, box, cutoff, feat_np=None, n_frames=1, out=None):
+        n = pos_f64_np.shape[0]
+        if out is None:
+            out = np.empty((n, 3), dtype=np.float64)
+        self._check(self.lib.gamd_compute_forces_host(self._h, _ptr(pos_f64_np), n, n_frames, _box3(box),
+                                                      float(cutoff), _ptr(feat_np), _ptr(out)))
+        return out
+
+    def vv_first_half(self, x, v, f, mass, dt):
+        self._check(self.lib.gamd_vv_first_half(self._h, _ptr(x), _ptr(v), _ptr(f), _ptr(mass), x.shape[0], float(dt),
+                                                _stream()))
+
+    def vv_second_half(self, v, f, mass, dt):
+        self._check(self.lib.gamd_vv_second_half(self._h, _ptr(v), _ptr(f), _ptr(mass), v.shape[0], float(dt),
+                                                 _stream()))
+
+    def md_run(self, x, v, f, mass, box, cutoff, dt, n_steps, feat=None, n_frames=1, ke=None):
+        self._check(self.lib.gamd_md_run(self._h, _ptr(x), _ptr(v), _ptr(f), _ptr(mass), x.shape[0], n_frames,
+                                         _box3(box), float(cutoff), _ptr(feat), float(dt), int(n_steps), _ptr(ke),
+                                         _stream()))
+
+    def md_step_host(self, x, v, f, mass, box, cutoff, dt, feat=None, n_frames=1):
+        self._check(self.lib.gamd_md_step_host(self._h, _ptr(x), _ptr(v), _ptr(f), _ptr(mass), x.shape[0], n_frames,
+                                               _box3(box), float(cutoff), _ptr(feat), float(dt)))
+
+    def check_async_errors(self):
+        self._check(self.lib.gamd_check_async_errors(self._h, _stream()))
+
+    def debug_tensor(self, name, dtype, shape):
+        """A torch view of a scratch buffer (tests / profiling only)."""
+        import torch
+        p, nb = c_void_p(), c_int64()
+        self._check(self.lib.gamd_debug_ptr(self._h, name.encode(), ctypes.byref(p), ctypes.byref(nb)))
+        count = int(np.prod(shape))
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        assert count * itemsize <= nb.value, (name, count * itemsize, nb.value)
+        iface = {"shape": (count * itemsize,), "typestr": "|u1", "data": (p.value, False), "version": 2}
+
+        class _W:
+            __cuda_array_interface__ = iface
+        t = torch.as_tensor(_W(), device=torch.device("cuda", self.device))
+        return t.view(dtype).view(*shape).clone()
+
+    @property
+    def launch_count(self):
+        return int(self.lib.gamd_launch_count(self._h))

@@ -1,0 +1,600 @@
+// C ABI of libgamd_b200 (see include/gamd_b200.h for the contract of every entry point).
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+
+static std::string g_create_err;
+
+namespace {
+
+struct WSpec {
+  std::string name;
+  int64_t rows, cols;   // cols == 0 -> vector of `rows`
+};
+
+std::vector<WSpec> expected_weights(const gamd_model_desc& d) {
+  std::vector<WSpec> v;
+  const int D = d.encoding_size, H = d.hidden_dim, De = d.edge_dim;
+  const int n_in = 4 + (d.expand_edge ? GAMD_NRBF : 0) + (d.use_bond ? 1 : 0);
+  v.push_back({"length_mean", 1, 0});
+  v.push_back({"length_std", 1, 0});
+  if (d.kind == GAMD_MODEL_LJ) v.push_back({"node_emb", 1, D});
+  for (int l = 0; l < d.conv_layer; l++) {
+    std::string p = "graph_conv.conv." + std::to_string(l) + ".";
+    auto lin = [&](const std::string& n, int64_t out, int64_t in) {
+      v.push_back({p + n + ".weight", out, in});
+      v.push_back({p + n + ".bias", out, 0});
+    };
+    lin("edge_affine.mlp_layer.0", 128, De);
+    lin("edge_affine.mlp_layer.2", H, 128);
+    lin("src_affine", H, D);
+    lin("dst_affine", H, D);
+    lin("theta_edge.mlp_layer.1", H, H);
+    lin("theta_edge.mlp_layer.3", D, H);
+    lin("phi_dst", H, D);
+    lin("phi_edge", H, D);
+    lin("phi.mlp_layer.1", D, H);
+  }
+  for (int l = 0; l < d.conv_layer; l++) {
+    v.push_back({"graph_conv.norm_layers." + std::to_string(l) + ".weight", D, 0});
+    v.push_back({"graph_conv.norm_layers." + std::to_string(l) + ".bias", D, 0});
+  }
+  if (d.expand_edge) v.push_back({"edge_expand.centers", GAMD_NRBF, 0});
+  if (d.kind != GAMD_MODEL_LJ) {
+    v.push_back({"node_encoder.weight", D, d.in_feats});
+    v.push_back({"node_encoder.bias", D, 0});
+  }
+  v.push_back({"edge_encoder.mlp_layer.0.weight", H, n_in});
+  v.push_back({"edge_encoder.mlp_layer.0.bias", H, 0});
+  v.push_back({"edge_encoder.mlp_layer.2.weight", H, H});
+  v.push_back({"edge_encoder.mlp_layer.2.bias", H, 0});
+  v.push_back({"edge_encoder.mlp_layer.4.weight", De, H});
+  v.push_back({"edge_encoder.mlp_layer.4.bias", De, 0});
+  v.push_back({"edge_layer_norm.weight", De, 0});
+  v.push_back({"edge_layer_norm.bias", De, 0});
+  v.push_back({"graph_decoder.mlp_layer.0.weight", H, D});
+  v.push_back({"graph_decoder.mlp_layer.0.bias", H, 0});
+  v.push_back({"graph_decoder.mlp_layer.2.weight", 3, H});
+  v.push_back({"graph_decoder.mlp_layer.2.bias", 3, 0});
+  return v;
+}
+
+// bump allocator over the arena, 256-byte aligned
+struct Carver {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+void carve(gamd_ctx* ctx, Carver& c, int64_t A, int64_t E) {
+  const int64_t rs_blocks = (A + 2047) / 2048 + 1;
+  ctx->cap_cells = 8 * A + 1024;
+  for (int i = 0; i < 2; i++) {
+    ctx->keys[i] = c.take<uint32_t>(A);
+    ctx->vals[i] = c.take<uint32_t>(A);
+  }
+  ctx->radix_hist = c.take<uint32_t>(2 * (256 * rs_blocks + 16));
+  ctx->scan_tmp = c.take<uint32_t>((A + 1) / 1024 + rs_blocks + 4096);
+  ctx->pos_nbr = c.take<float4>(A);
+  ctx->pos_feat = c.take<float4>(A);
+  ctx->pos_nbr_s = c.take<float4>(A);
+  ctx->pos_feat_s = c.take<float4>(A);
+  ctx->perm = c.take<int>(A);
+  ctx->cell_start = c.take<int>(ctx->cap_cells + 1);
+  ctx->deg = c.take<int>(A + 1);
+  ctx->row_ptr = c.take<int>(A + 1);
+  ctx->deg_o = c.take<int>(A + 1);
+  ctx->row_ptr_o = c.take<int>(A + 1);
+  ctx->n_edges = c.take<int>(4);
+  ctx->err_flag = c.take<int>(4);
+  ctx->col_idx = c.take<int>(E);
+  ctx->edge_dst = c.take<int>(E);
+  ctx->e_emb = c.take<float>((size_t)E * GAMD_NF);
+  ctx->h = c.take<float>((size_t)A * GAMD_NF);
+  ctx->hn = c.take<float>((size_t)A * GAMD_NF);
+  ctx->srcA = c.take<float>((size_t)A * GAMD_NF);
+  ctx->dstA = c.take<float>((size_t)A * GAMD_NF);
+  ctx->pd = c.take<float>((size_t)A * GAMD_NF);
+  ctx->agg = c.take<float>((size_t)A * GAMD_NF);
+  ctx->part = c.take<float>((size_t)(E / GAMD_EDGE_TILE + 2) * 2 * GAMD_NF);
+  ctx->pred = c.take<float>((size_t)A * 3);
+  ctx->feat_s = c.take<float>(A);
+  ctx->stage_a = c.take<double>((size_t)A * 3);
+  ctx->stage_b = c.take<double>((size_t)A * 3);
+  ctx->stage_c = c.take<double>((size_t)A * 3);
+  ctx->stage_m = c.take<double>(A);
+  ctx->stage_feat = c.take<float>(A);
+}
+
+__global__ void k_pack_pos_feat(const float* __restrict__ pos, const float* __restrict__ feat, int64_t n,
+                                float4* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], feat ? feat[i] : 0.f);
+}
+
+int check_ready(gamd_ctx* ctx) {
+  if (!ctx) return GAMD_EINVAL;
+  if (!ctx->finalized) {
+    ctx->err = "weights not finalized: call gamd_load_weight for every tensor, then gamd_finalize_weights";
+    return GAMD_ESTATE;
+  }
+  if (!ctx->arena) {
+    ctx->err = "no scratch reserved: call gamd_reserve";
+    return GAMD_ESTATE;
+  }
+  return 0;
+}
+
+int positions_to_forces(gamd_ctx* ctx, const double* d_x, double scale, int64_t n, int n_frames, const double box[3],
+                        float cutoff, const float* d_feat, cudaStream_t st) {
+  float boxf[3] = {(float)box[0], (float)box[1], (float)box[2]};
+  NbrParams p;
+  int rc = nbr_setup_params(ctx, n, n_frames, boxf, cutoff, GAMD_NBR_LT | GAMD_NBR_SELF, &p);
+  if (rc) return rc;
+  if ((rc = nbr_bin_f64(ctx, d_x, scale, box, p, st))) return rc;
+  if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
+  return model_forward_fp32(ctx, ctx->pos_feat_s, nullptr, ctx->perm, n, p.atoms_per_frame, boxf, st);
+}
+
+}  // namespace
+
+int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st) {
+  k_pack_pos_feat<<<ceil_div(n, 256), 256, 0, st>>>(d_pos, d_feat, n, out);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" {
+
+const char* gamd_version(void) { return "gamd_b200 0.1 (sm_100a)"; }
+
+const char* gamd_last_error(const gamd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
+  if (!desc || !out) {
+    g_create_err = "null argument";
+    return GAMD_EINVAL;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    g_create_err = std::string("no usable CUDA device (there is no CPU fallback): ") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+    return GAMD_ENOGPU;
+  }
+  if (desc->encoding_size != GAMD_NF || desc->hidden_dim != GAMD_NF || desc->edge_dim != GAMD_NF) {
+    g_create_err = "only encoding_size = hidden_dim = edge_embedding_dim = 128 is built";
+    return GAMD_EUNSUPPORTED;
+  }
+  if (desc->conv_layer < 1 || desc->conv_layer > 8) {
+    g_create_err = "conv_layer must be in 1..8";
+    return GAMD_EUNSUPPORTED;
+  }
+  if (desc->kind != GAMD_MODEL_LJ && desc->in_feats != 1) {
+    g_create_err = "node_encoder in_feats must be 1";
+    return GAMD_EUNSUPPORTED;
+  }
+  if (desc->precision != GAMD_PREC_FP32) {
+    g_create_err = "precision mode not built yet";
+    return GAMD_EUNSUPPORTED;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    return GAMD_ECUDA;
+  }
+  gamd_ctx* ctx = new gamd_ctx();
+  ctx->device = device;
+  ctx->desc = *desc;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return 0;
+}
+
+int gamd_destroy(gamd_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->d_wblob) cudaFree(ctx->d_wblob);
+  if (ctx->d_bond) cudaFree(ctx->d_bond);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  delete ctx;
+  return 0;
+}
+
+int gamd_reserve(gamd_ctx* ctx, int64_t max_atoms, int64_t max_edges) {
+  if (!ctx || max_atoms <= 0 || max_edges < 0) return GAMD_EINVAL;
+  if (max_atoms >= (int64_t(1) << 30) || max_edges >= (int64_t(1) << 31) - 64) {
+    ctx->err = "capacity exceeds 32-bit indexing";
+    return GAMD_EUNSUPPORTED;
+  }
+  GAMD_CUDA(cudaSetDevice(ctx->device));
+  if (max_atoms <= ctx->cap_atoms && max_edges <= ctx->cap_edges) return 0;
+  if (max_atoms < ctx->cap_atoms) max_atoms = ctx->cap_atoms;
+  if (max_edges < ctx->cap_edges) max_edges = ctx->cap_edges;
+  Carver dry{nullptr};
+  carve(ctx, dry, max_atoms, max_edges);
+  size_t bytes = dry.off + 256;
+  GAMD_CUDA(cudaDeviceSynchronize());
+  if (ctx->arena) GAMD_CUDA(cudaFree(ctx->arena));
+  ctx->arena = nullptr;
+  ctx->cap_atoms = ctx->cap_edges = 0;
+  cudaError_t e = cudaMalloc(&ctx->arena, bytes);
+  if (e != cudaSuccess) {
+    ctx->arena = nullptr;
+    ctx->err = "cudaMalloc of " + std::to_string(bytes) + " bytes of scratch failed: " + cudaGetErrorString(e);
+    return GAMD_ECUDA;
+  }
+  ctx->arena_bytes = bytes;
+  Carver real{static_cast<char*>(ctx->arena)};
+  carve(ctx, real, max_atoms, max_edges);
+  ctx->cap_atoms = max_atoms;
+  ctx->cap_edges = max_edges;
+  GAMD_CUDA(cudaMemset(ctx->err_flag, 0, 4 * sizeof(int)));
+  GAMD_CUDA(cudaMemset(ctx->n_edges, 0, 4 * sizeof(int)));
+  size_t pin = sizeof(double) * 3 * (size_t)max_atoms;
+  if (pin > ctx->pinned_bytes) {
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+  }
+  ctx->last_nbr = NbrParams{};
+  return 0;
+}
+
+int gamd_load_weight(gamd_ctx* ctx, const char* name, const float* h_data, int64_t n) {
+  if (!ctx || !name || !h_data || n <= 0) return GAMD_EINVAL;
+  for (const auto& w : expected_weights(ctx->desc)) {
+    if (w.name == name) {
+      int64_t want = w.rows * (w.cols ? w.cols : 1);
+      if (want != n) {
+        ctx->err = std::string("size mismatch for ") + name + ": got " + std::to_string(n) + ", expected " +
+                   std::to_string(want);
+        return GAMD_EINVAL;
+      }
+      ctx->host_w[name] = std::vector<float>(h_data, h_data + n);
+      ctx->finalized = false;
+      return 0;
+    }
+  }
+  ctx->err = std::string("unexpected state-dict key: ") + name;
+  return GAMD_EINVAL;
+}
+
+int gamd_set_scaler(gamd_ctx* ctx, double mean, double var) {
+  if (!ctx || !(var >= 0.0)) return GAMD_EINVAL;
+  ctx->scaler_mean = mean;
+  ctx->scaler_var = var;
+  return 0;
+}
+
+int gamd_set_bonds(gamd_ctx* ctx, const int64_t* h_bonds, int64_t nb, int64_t n_atoms_per_frame) {
+  if (!ctx || nb < 0 || n_atoms_per_frame <= 0 || (nb > 0 && !h_bonds)) return GAMD_EINVAL;
+  GAMD_CUDA(cudaSetDevice(ctx->device));
+  std::vector<int> tab((size_t)n_atoms_per_frame * GAMD_MAX_BOND, -1);
+  auto add = [&](int64_t a, int64_t b) -> bool {
+    for (int k = 0; k < GAMD_MAX_BOND; k++) {
+      int& slot = tab[(size_t)a * GAMD_MAX_BOND + k];
+      if (slot == (int)b) return true;
+      if (slot < 0) {
+        slot = (int)b;
+        return true;
+      }
+    }
+    return false;
+  };
+  for (int64_t i = 0; i < nb; i++) {
+    int64_t a = h_bonds[2 * i], b = h_bonds[2 * i + 1];
+    if (a < 0 || b < 0 || a >= n_atoms_per_frame || b >= n_atoms_per_frame) {
+      ctx->err = "bond index out of range";
+      return GAMD_EINVAL;
+    }
+    if (!add(a, b) || !add(b, a)) {
+      ctx->err = "more than 4 bonded partners per atom are not supported";
+      return GAMD_EUNSUPPORTED;
+    }
+  }
+  if (ctx->d_bond) cudaFree(ctx->d_bond);
+  ctx->d_bond = nullptr;
+  GAMD_CUDA(cudaMalloc(&ctx->d_bond, tab.size() * sizeof(int)));
+  GAMD_CUDA(cudaMemcpy(ctx->d_bond, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ctx->bond_atoms = n_atoms_per_frame;
+  return 0;
+}
+
+int gamd_finalize_weights(gamd_ctx* ctx) {
+  if (!ctx) return GAMD_EINVAL;
+  GAMD_CUDA(cudaSetDevice(ctx->device));
+  const gamd_model_desc& d = ctx->desc;
+  auto specs = expected_weights(d);
+  for (const auto& w : specs)
+    if (!ctx->host_w.count(w.name)) {
+      ctx->err = "missing state-dict key: " + w.name;
+      return GAMD_ESTATE;
+    }
+  std::vector<float> blob;
+  std::vector<std::pair<const float**, size_t>> fix;  // pointer slots to patch with blob offsets
+  auto push = [&](const float** slot, const std::vector<float>& v) {
+    while (blob.size() % 64) blob.push_back(0.f);  // 256-byte alignment for cp.async / float4
+    fix.push_back({slot, blob.size()});
+    blob.insert(blob.end(), v.begin(), v.end());
+  };
+  auto transposed = [&](const std::string& name, int64_t out, int64_t in, int64_t pad_in) {
+    const std::vector<float>& w = ctx->host_w[name];
+    std::vector<float> t((size_t)pad_in * out, 0.f);
+    for (int64_t o = 0; o < out; o++)
+      for (int64_t k = 0; k < in; k++) t[(size_t)k * out + o] = w[(size_t)o * in + k];
+    return t;
+  };
+  ModelW& mw = ctx->mw;
+  mw = ModelW{};
+  const int NFv = GAMD_NF;
+  for (int l = 0; l < d.conv_layer; l++) {
+    std::string p = "graph_conv.conv." + std::to_string(l) + ".";
+    LayerW& L = mw.layer[l];
+    push(&L.ea0_t, transposed(p + "edge_affine.mlp_layer.0.weight", NFv, NFv, NFv));
+    push(&L.ea0_b, ctx->host_w[p + "edge_affine.mlp_layer.0.bias"]);
+    push(&L.ea2_t, transposed(p + "edge_affine.mlp_layer.2.weight", NFv, NFv, NFv));
+    push(&L.ea2_b, ctx->host_w[p + "edge_affine.mlp_layer.2.bias"]);
+    push(&L.src_t, transposed(p + "src_affine.weight", NFv, NFv, NFv));
+    push(&L.src_b, ctx->host_w[p + "src_affine.bias"]);
+    push(&L.dst_t, transposed(p + "dst_affine.weight", NFv, NFv, NFv));
+    push(&L.dst_b, ctx->host_w[p + "dst_affine.bias"]);
+    push(&L.te1_t, transposed(p + "theta_edge.mlp_layer.1.weight", NFv, NFv, NFv));
+    push(&L.te1_b, ctx->host_w[p + "theta_edge.mlp_layer.1.bias"]);
+    push(&L.te3_t, transposed(p + "theta_edge.mlp_layer.3.weight", NFv, NFv, NFv));
+    push(&L.te3_b, ctx->host_w[p + "theta_edge.mlp_layer.3.bias"]);
+    push(&L.pdst_t, transposed(p + "phi_dst.weight", NFv, NFv, NFv));
+    push(&L.pdst_b, ctx->host_w[p + "phi_dst.bias"]);
+    push(&L.pedge_t, transposed(p + "phi_edge.weight", NFv, NFv, NFv));
+    push(&L.pedge_b, ctx->host_w[p + "phi_edge.bias"]);
+    push(&L.phi_t, transposed(p + "phi.mlp_layer.1.weight", NFv, NFv, NFv));
+    push(&L.phi_b, ctx->host_w[p + "phi.mlp_layer.1.bias"]);
+    push(&L.ln_w, ctx->host_w["graph_conv.norm_layers." + std::to_string(l) + ".weight"]);
+    push(&L.ln_b, ctx->host_w["graph_conv.norm_layers." + std::to_string(l) + ".bias"]);
+  }
+  const int n_in = 4 + (d.expand_edge ? GAMD_NRBF : 0) + (d.use_bond ? 1 : 0);
+  push(&mw.enc0_t, transposed("edge_encoder.mlp_layer.0.weight", NFv, n_in, 64));
+  push(&mw.enc0_b, ctx->host_w["edge_encoder.mlp_layer.0.bias"]);
+  push(&mw.enc2_t, transposed("edge_encoder.mlp_layer.2.weight", NFv, NFv, NFv));
+  push(&mw.enc2_b, ctx->host_w["edge_encoder.mlp_layer.2.bias"]);
+  push(&mw.enc4_t, transposed("edge_encoder.mlp_layer.4.weight", NFv, NFv, NFv));
+  push(&mw.enc4_b, ctx->host_w["edge_encoder.mlp_layer.4.bias"]);
+  push(&mw.eln_w, ctx->host_w["edge_layer_norm.weight"]);
+  push(&mw.eln_b, ctx->host_w["edge_layer_norm.bias"]);
+  push(&mw.dec0_t, transposed("graph_decoder.mlp_layer.0.weight", NFv, NFv, NFv));
+  push(&mw.dec0_b, ctx->host_w["graph_decoder.mlp_layer.0.bias"]);
+  push(&mw.dec2_w, ctx->host_w["graph_decoder.mlp_layer.2.weight"]);
+  push(&mw.dec2_b, ctx->host_w["graph_decoder.mlp_layer.2.bias"]);
+  if (d.kind == GAMD_MODEL_LJ) {
+    push(&mw.node_emb, ctx->host_w["node_emb"]);
+  } else {
+    push(&mw.nenc_w, ctx->host_w["node_encoder.weight"]);
+    push(&mw.nenc_b, ctx->host_w["node_encoder.bias"]);
+  }
+  if (d.expand_edge) push(&mw.centers, ctx->host_w["edge_expand.centers"]);
+  mw.length_mean = ctx->host_w["length_mean"][0];
+  mw.length_std = ctx->host_w["length_std"][0];
+  mw.n_layers = d.conv_layer;
+  mw.n_edge_in = n_in;
+  mw.use_bond = d.use_bond;
+  mw.expand_edge = d.expand_edge;
+  mw.kind = d.kind;
+  if (ctx->d_wblob) cudaFree(ctx->d_wblob);
+  ctx->d_wblob = nullptr;
+  GAMD_CUDA(cudaMalloc(&ctx->d_wblob, blob.size() * sizeof(float)));
+  GAMD_CUDA(cudaMemcpy(ctx->d_wblob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  for (auto& f : fix) *f.first = ctx->d_wblob + f.second;
+  if (d.use_bond && !ctx->d_bond) {
+    ctx->err = "model uses the bond flag: call gamd_set_bonds before gamd_finalize_weights";
+    return GAMD_ESTATE;
+  }
+  ctx->finalized = true;
+  return 0;
+}
+
+int gamd_check_async_errors(gamd_ctx* ctx, void* stream) {
+  if (!ctx || !ctx->arena) return GAMD_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  int flag[4] = {0, 0, 0, 0};
+  int ne = 0;
+  GAMD_CUDA(cudaMemcpyAsync(flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GAMD_CUDA(cudaMemcpyAsync(&ne, ctx->n_edges, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GAMD_CUDA(cudaStreamSynchronize(st));
+  if (flag[0]) GAMD_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), st));
+  if (flag[0] & 1) {
+    ctx->err = "edge capacity exceeded: " + std::to_string(ne) + " edges needed, " + std::to_string(ctx->cap_edges) +
+               " reserved; call gamd_reserve with a larger max_edges";
+    return GAMD_ECAPACITY;
+  }
+  if (flag[0] & 2) {
+    ctx->err = "edge list must be sorted by centre with ids in [0, n_atoms)";
+    return GAMD_EINVAL;
+  }
+  return 0;
+}
+
+int gamd_neighbor_build(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, int32_t n_frames, const double h_box[3],
+                        float cutoff, int32_t flags, void* stream) {
+  if (!ctx || !d_pos || !h_box) return GAMD_EINVAL;
+  if (!ctx->arena) {
+    ctx->err = "no scratch reserved: call gamd_reserve";
+    return GAMD_ESTATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float boxf[3] = {(float)h_box[0], (float)h_box[1], (float)h_box[2]};
+  NbrParams p;
+  int rc = nbr_setup_params(ctx, n_atoms, n_frames, boxf, cutoff, flags, &p);
+  if (rc) return rc;
+  if ((rc = nbr_bin_f32(ctx, d_pos, p, st))) return rc;
+  return nbr_sort_and_sweep(ctx, p, nullptr, st);
+}
+
+int gamd_neighbor_count_host(gamd_ctx* ctx, int64_t* n_edges, void* stream) {
+  if (!ctx || !n_edges || !ctx->arena) return GAMD_EINVAL;
+  int rc = gamd_check_async_errors(ctx, stream);
+  int ne = 0;
+  GAMD_CUDA(cudaMemcpy(&ne, ctx->n_edges, sizeof(int), cudaMemcpyDeviceToHost));
+  *n_edges = ne;
+  return rc;
+}
+
+int gamd_neighbor_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float* d_dist, float* d_norm,
+                         void* stream) {
+  if (!ctx || !d_edge_idx || !ctx->arena) return GAMD_EINVAL;
+  return nbr_export(ctx, d_edge_idx, cap, d_dist, d_norm, (cudaStream_t)stream);
+}
+
+int gamd_model_forward(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, int32_t n_frames, const double h_box[3],
+                       const int64_t* d_center, const int64_t* d_neigh, int64_t n_edges, const float* d_feat,
+                       float* d_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!d_pos || !h_box || !d_out || n_atoms <= 0 || n_frames <= 0 || n_atoms % n_frames || n_edges < 0 ||
+      (n_edges > 0 && (!d_center || !d_neigh)))
+    return GAMD_EINVAL;
+  if (ctx->desc.kind != GAMD_MODEL_LJ && !d_feat) {
+    ctx->err = "this model needs the node feature vector";
+    return GAMD_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = csr_from_sorted_coo(ctx, d_center, d_neigh, n_atoms, n_edges, st))) return rc;
+  if ((rc = pack_pos_feat(ctx, d_pos, d_feat, n_atoms, ctx->pos_feat_s, st))) return rc;
+  float boxf[3] = {(float)h_box[0], (float)h_box[1], (float)h_box[2]};
+  if ((rc = model_forward_fp32(ctx, ctx->pos_feat_s, nullptr, nullptr, n_atoms, (int)(n_atoms / n_frames), boxf, st)))
+    return rc;
+  GAMD_CUDA(cudaMemcpyAsync(d_out, ctx->pred, sizeof(float) * 3 * n_atoms, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int gamd_compute_forces(gamd_ctx* ctx, const double* d_pos, int64_t n_atoms, int32_t n_frames, const double h_box[3],
+                        float cutoff, const float* d_feat, double* d_force, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!d_pos || !h_box || !d_force) return GAMD_EINVAL;
+  if (ctx->desc.kind != GAMD_MODEL_LJ && !d_feat) {
+    ctx->err = "this model needs the node feature vector";
+    return GAMD_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = positions_to_forces(ctx, d_pos, 1.0, n_atoms, n_frames, h_box, cutoff, d_feat, st))) return rc;
+  return integ_denorm_scatter(ctx, ctx->perm, d_force, nullptr, nullptr, 0.0, n_atoms, nullptr, st);
+}
+
+int gamd_compute_forces_host(gamd_ctx* ctx, const double* h_pos, int64_t n_atoms, int32_t n_frames,
+                             const double h_box[3], float cutoff, const float* h_feat, double* h_force) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!h_pos || !h_force || n_atoms <= 0) return GAMD_EINVAL;
+  if (n_atoms > ctx->cap_atoms) {
+    ctx->err = "n_atoms exceeds reserved capacity; call gamd_reserve";
+    return GAMD_ECAPACITY;
+  }
+  GAMD_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = 0;
+  size_t b3 = sizeof(double) * 3 * (size_t)n_atoms;
+  GAMD_CUDA(cudaMemcpyAsync(ctx->stage_a, h_pos, b3, cudaMemcpyHostToDevice, st));
+  if (h_feat) GAMD_CUDA(cudaMemcpyAsync(ctx->stage_feat, h_feat, sizeof(float) * n_atoms, cudaMemcpyHostToDevice, st));
+  if ((rc = gamd_compute_forces(ctx, ctx->stage_a, n_atoms, n_frames, h_box, cutoff, h_feat ? ctx->stage_feat : nullptr,
+                                ctx->stage_b, st)))
+    return rc;
+  GAMD_CUDA(cudaMemcpyAsync(h_force, ctx->stage_b, b3, cudaMemcpyDeviceToHost, st));
+  return gamd_check_async_errors(ctx, st);
+}
+
+int gamd_vv_first_half(gamd_ctx* ctx, double* d_x, double* d_v, const double* d_f, const double* d_mass,
+                       int64_t n_atoms, double dt, void* stream) {
+  if (!ctx || !d_x || !d_v || !d_f || !d_mass || n_atoms <= 0) return GAMD_EINVAL;
+  return integ_first_half(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, (cudaStream_t)stream);
+}
+
+int gamd_vv_second_half(gamd_ctx* ctx, double* d_v, const double* d_f, const double* d_mass, int64_t n_atoms,
+                        double dt, void* stream) {
+  if (!ctx || !d_v || !d_f || !d_mass || n_atoms <= 0) return GAMD_EINVAL;
+  return integ_second_half(ctx, d_v, d_f, d_mass, n_atoms, dt, (cudaStream_t)stream);
+}
+
+int gamd_md_run(gamd_ctx* ctx, double* d_x, double* d_v, double* d_f, const double* d_mass, int64_t n_atoms,
+                int32_t n_frames, const double h_box[3], float cutoff, const float* d_feat, double dt,
+                int32_t n_steps, double* d_ke, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!d_x || !d_v || !d_f || !d_mass || !h_box || n_steps < 0) return GAMD_EINVAL;
+  if (ctx->desc.kind != GAMD_MODEL_LJ && !d_feat) {
+    ctx->err = "this model needs the node feature vector";
+    return GAMD_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = 0; s < n_steps; s++) {
+    if ((rc = integ_first_half(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, st))) return rc;
+    // forces at x*10 Angstrom (test_nosehoover.py:112: value_in_unit(angstrom))
+    if ((rc = positions_to_forces(ctx, d_x, 10.0, n_atoms, n_frames, h_box, cutoff, d_feat, st))) return rc;
+    if ((rc = integ_denorm_scatter(ctx, ctx->perm, d_f, d_v, d_mass, dt, n_atoms, d_ke ? d_ke + s : nullptr, st)))
+      return rc;
+  }
+  return 0;
+}
+
+int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, const double* h_mass, int64_t n_atoms,
+                      int32_t n_frames, const double h_box[3], float cutoff, const float* h_feat, double dt) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!h_x || !h_v || !h_f || !h_mass || n_atoms <= 0) return GAMD_EINVAL;
+  if (n_atoms > ctx->cap_atoms) {
+    ctx->err = "n_atoms exceeds reserved capacity; call gamd_reserve";
+    return GAMD_ECAPACITY;
+  }
+  GAMD_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = 0;
+  size_t b3 = sizeof(double) * 3 * (size_t)n_atoms;
+  GAMD_CUDA(cudaMemcpyAsync(ctx->stage_a, h_x, b3, cudaMemcpyHostToDevice, st));
+  GAMD_CUDA(cudaMemcpyAsync(ctx->stage_b, h_v, b3, cudaMemcpyHostToDevice, st));
+  GAMD_CUDA(cudaMemcpyAsync(ctx->stage_c, h_f, b3, cudaMemcpyHostToDevice, st));
+  GAMD_CUDA(cudaMemcpyAsync(ctx->stage_m, h_mass, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, st));
+  if (h_feat) GAMD_CUDA(cudaMemcpyAsync(ctx->stage_feat, h_feat, sizeof(float) * n_atoms, cudaMemcpyHostToDevice, st));
+  if ((rc = gamd_md_run(ctx, ctx->stage_a, ctx->stage_b, ctx->stage_c, ctx->stage_m, n_atoms, n_frames, h_box, cutoff,
+                        h_feat ? ctx->stage_feat : nullptr, dt, 1, nullptr, st)))
+    return rc;
+  GAMD_CUDA(cudaMemcpyAsync(h_x, ctx->stage_a, b3, cudaMemcpyDeviceToHost, st));
+  GAMD_CUDA(cudaMemcpyAsync(h_v, ctx->stage_b, b3, cudaMemcpyDeviceToHost, st));
+  GAMD_CUDA(cudaMemcpyAsync(h_f, ctx->stage_c, b3, cudaMemcpyDeviceToHost, st));
+  return gamd_check_async_errors(ctx, st);
+}
+
+int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_bytes) {
+  if (!ctx || !name || !d_ptr || !ctx->arena) return GAMD_EINVAL;
+  std::string n(name);
+  const int64_t A = ctx->cap_atoms, E = ctx->cap_edges;
+  int64_t nb = 0;
+  void* p = nullptr;
+  if (n == "row_ptr") p = ctx->row_ptr, nb = 4 * (A + 1);
+  else if (n == "col_idx") p = ctx->col_idx, nb = 4 * E;
+  else if (n == "edge_dst") p = ctx->edge_dst, nb = 4 * E;
+  else if (n == "perm") p = ctx->perm, nb = 4 * A;
+  else if (n == "n_edges") p = ctx->n_edges, nb = 4;
+  else if (n == "pos_sorted") p = ctx->pos_feat_s, nb = 16 * A;
+  else if (n == "pos_nbr_sorted") p = ctx->pos_nbr_s, nb = 16 * A;
+  else if (n == "e_emb") p = ctx->e_emb, nb = 4 * E * GAMD_NF;
+  else if (n == "h") p = ctx->h, nb = 4 * A * GAMD_NF;
+  else if (n == "hn") p = ctx->hn, nb = 4 * A * GAMD_NF;
+  else if (n == "agg") p = ctx->agg, nb = 4 * A * GAMD_NF;
+  else if (n == "pred") p = ctx->pred, nb = 4 * A * 3;
+  else {
+    ctx->err = "unknown debug buffer: " + n;
+    return GAMD_EINVAL;
+  }
+  *d_ptr = p;
+  if (n_bytes) *n_bytes = nb;
+  return 0;
+}
+
+int64_t gamd_launch_count(const gamd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// Shared declarations of libgamd_b200: context, scratch arena, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <map>
+#include <vector>
+#include "../../include/gamd_b200.h"
+
+#define GAMD_NF 128          // feature width the kernels are built for (D = H = De = 128)
+#define GAMD_EDGE_TILE 64    // edges per tile of the fp32 edge kernels
+#define GAMD_NODE_TILE 64    // nodes per tile of the node kernels
+#define GAMD_MAX_BOND 4      // bonded partners kept per atom (water: O has 2, H has 1)
+#define GAMD_NRBF 40
+
+struct NbrParams {
+  float box[3], half[3], inv_cell[3];
+  int nc[3];
+  int cells_per_frame;
+  int n_atoms, atoms_per_frame, n_frames;
+  float rc, rc2;
+  int flags;
+};
+
+// device copies of one message-passing layer's weights (transposed: Wt[k][n] = W[n][k])
+struct LayerW {
+  const float *ea0_t, *ea0_b, *ea2_t, *ea2_b;
+  const float *src_t, *src_b, *dst_t, *dst_b;
+  const float *te1_t, *te1_b, *te3_t, *te3_b;
+  const float *pdst_t, *pdst_b, *pedge_t, *pedge_b;
+  const float *phi_t, *phi_b;
+  const float *ln_w, *ln_b;
+};
+
+struct ModelW {
+  LayerW layer[8];
+  const float *enc0_t, *enc0_b, *enc2_t, *enc2_b, *enc4_t, *enc4_b, *eln_w, *eln_b;  // enc0_t is [64][128], zero padded
+  const float *dec0_t, *dec0_b, *dec2_w, *dec2_b;   // dec2_w stays [3][128]
+  const float *node_emb;                             // [128] (LJ)
+  const float *nenc_w, *nenc_b;                      // [128] each (water, in_feats = 1)
+  const float *centers;                              // [40]
+  float length_mean, length_std;
+  int n_layers, n_edge_in, use_bond, expand_edge, kind;
+};
+
+struct gamd_ctx {
+  int device = 0;
+  gamd_model_desc desc{};
+  std::string err;
+  int64_t launches = 0;
+
+  // host-side weights by reference state-dict name
+  std::map<std::string, std::vector<float>> host_w;
+  bool finalized = false;
+  float* d_wblob = nullptr;
+  ModelW mw{};
+  double scaler_mean = 0.0, scaler_var = 1.0;
+  int* d_bond = nullptr;          // [atoms_per_frame][GAMD_MAX_BOND] frame-local partner ids, -1 padded
+  int64_t bond_atoms = 0;
+
+  // scratch
+  int64_t cap_atoms = 0, cap_edges = 0;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  // neighbor
+  uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+  uint32_t* radix_hist = nullptr;
+  uint32_t* scan_tmp = nullptr;
+  float4 *pos_nbr = nullptr, *pos_feat = nullptr;             // caller order
+  float4 *pos_nbr_s = nullptr, *pos_feat_s = nullptr;         // cell-sorted order
+  int* perm = nullptr;                                        // sorted index -> caller index
+  int* cell_start = nullptr;
+  int64_t cap_cells = 0;
+  int *deg = nullptr, *row_ptr = nullptr, *col_idx = nullptr, *edge_dst = nullptr;
+  int* n_edges = nullptr;                                     // device scalar (== row_ptr[n])
+  int* err_flag = nullptr;                                    // device: bit0 edge overflow
+  // model
+  float *e_emb = nullptr, *h = nullptr, *hn = nullptr, *srcA = nullptr, *dstA = nullptr, *pd = nullptr;
+  float *agg = nullptr, *part = nullptr, *pred = nullptr;
+  float* feat_s = nullptr;                                    // node type feature in sorted order
+  // export helpers
+  int *deg_o = nullptr, *row_ptr_o = nullptr;
+  // host staging
+  double *stage_a = nullptr, *stage_b = nullptr, *stage_c = nullptr, *stage_m = nullptr;
+  float* stage_feat = nullptr;
+  int64_t stage_atoms = 0;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  NbrParams last_nbr{};
+  int sm_count = 148;
+};
+
+#define GAMD_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                     \
+      return GAMD_ECUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define GAMD_LAUNCH_CHECK()                                                              \
+  do {                                                                                   \
+    ctx->launches++;                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      ctx->err = std::string("kernel launch at ") + __FILE__ + ":" + std::to_string(__LINE__) + ": " + cudaGetErrorString(_e); \
+      return GAMD_ECUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- stage entry points implemented in the .cu files (host functions) ----
+int nbr_setup_params(gamd_ctx* ctx, int64_t n_atoms, int n_frames, const float box[3], float rc, int flags, NbrParams* p);
+int nbr_bin_f32(gamd_ctx* ctx, const float* d_pos, const NbrParams& p, cudaStream_t st);
+int nbr_bin_f64(gamd_ctx* ctx, const double* d_pos_or_x, double scale, const double* box64, const NbrParams& p, cudaStream_t st);
+int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, cudaStream_t st);
+int nbr_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float* d_dist, float* d_norm, cudaStream_t st);
+int csr_from_sorted_coo(gamd_ctx* ctx, const int64_t* d_center, const int64_t* d_neigh, int64_t n_atoms, int64_t n_edges, cudaStream_t st);
+int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cudaStream_t st);
+
+int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* feat, const int* orig_id,
+                       int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st);
+
+int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
+int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
+int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt, int64_t n, double* ke_out, cudaStream_t st);
+int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st);

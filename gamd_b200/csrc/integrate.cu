@@ -1,0 +1,89 @@
+// Stage 3: integrator hook kernels (fp64 state, OpenMM units: nm, ps, Da, kJ/mol/nm).
+//
+// Restates the per-DOF programs of code/hack_integrator.py:
+//   first half   :271-277   v += 0.5*dt*force_last/m ; x += dt*v      (no constraints: the
+//                            v += (x-x1)/dt correction is identically zero)
+//   second half  :171-178 / :421-422   v += (dt/2)*gnn_force/m
+// and the force de-normalisation of code/LJ/train_network_lj.py:128-131, :153-155
+// (fp32 prediction * sqrt(var) + mean, in double), fused with the second half-kick and the
+// un-permutation from cell-sorted order back to the caller's atom order.
+#include "common.cuh"
+
+__global__ void k_vv_first(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ f,
+                           const double* __restrict__ mass, int64_t n, double dt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m = mass[i];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double vv = v[3 * i + k] + 0.5 * dt * f[3 * i + k] / m;
+    v[3 * i + k] = vv;
+    x[3 * i + k] = x[3 * i + k] + dt * vv;
+  }
+}
+
+__global__ void k_vv_second(double* __restrict__ v, const double* __restrict__ f, const double* __restrict__ mass,
+                            int64_t n, double dt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m = mass[i];
+#pragma unroll
+  for (int k = 0; k < 3; k++) v[3 * i + k] = v[3 * i + k] + (dt / 2) * f[3 * i + k] / m;
+}
+
+// pred (fp32, sorted order) -> f (fp64, caller order) [+ second half-kick] [+ kinetic energy]
+__global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __restrict__ perm, int64_t n,
+                                 double sigma, double mean, double* __restrict__ f, double* __restrict__ v,
+                                 const double* __restrict__ mass, double dt, double* __restrict__ ke) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double local = 0.0;
+  if (s < n) {
+    int64_t i = perm ? perm[s] : s;
+    double m = v ? mass[i] : 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double F = (double)pred[3 * s + k] * sigma + mean;
+      f[3 * i + k] = F;
+      if (v) {
+        double vv = v[3 * i + k] + (dt / 2) * F / m;
+        v[3 * i + k] = vv;
+        local += 0.5 * m * vv * vv;
+      }
+    }
+  }
+  if (ke) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ double sw[8];
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sw[w];
+      atomicAdd(ke, t);
+    }
+  }
+}
+
+int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt,
+                     cudaStream_t st) {
+  k_vv_first<<<ceil_div(n, 256), 256, 0, st>>>(x, v, f, mass, n, dt);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* mass, int64_t n, double dt,
+                      cudaStream_t st) {
+  k_vv_second<<<ceil_div(n, 256), 256, 0, st>>>(v, f, mass, n, dt);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt,
+                         int64_t n, double* ke_out, cudaStream_t st) {
+  if (ke_out) GAMD_CUDA(cudaMemsetAsync(ke_out, 0, sizeof(double), st));
+  k_denorm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(ctx->pred, perm, n, sqrt(ctx->scaler_var), ctx->scaler_mean,
+                                                     f_out, v, mass, dt, ke_out);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,612 @@
+// Stage 1: periodic cell-list neighbor search -> receiver-sorted CSR.
+//
+// Replaces jax-md's partition.neighbor_list + the exact mask + the COO conversion of the
+// reference (code/graph_utils.py:29-61, code/LJ/train_network_lj.py:166-199) and the O(N^2)
+// torch path (code/md_module.py:63-126).  Pipeline (no host synchronisation anywhere):
+//
+//   bin    wrap positions (fmod semantics of jnp.mod / np.mod), cell key per atom
+//   sort   stable LSD radix sort of (cell key, atom id), 8 bits per pass
+//   gather float4 positions in cell order, cell_start table
+//   count  one warp per centre, 27-cell sweep over contiguous x-runs, exact fp32 predicate
+//   scan   degrees -> row_ptr
+//   fill   same sweep, warp-ballot compaction straight into col_idx / edge_dst
+//
+// The predicate is evaluated for every DIRECTED pair from its own centre, one IEEE rounding
+// per operation (no FMA contraction), so the edge set is bit-identical to oracle/neighbor.py.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// arithmetic shared by bin / sweep / export
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float wrap_pos(float x, float L) {
+  // jnp.mod / np.mod / torch.remainder: fmod, then add L when the sign differs (L > 0)
+  float r = fmodf(x, L);
+  if (r < 0.f) r = __fadd_rn(r, L);
+  return r + 0.f;  // -0 -> +0
+}
+
+template <bool GENERAL>
+__device__ __forceinline__ float min_image(float t, float L, float half) {
+  // jax-md periodic_displacement: mod(dR + L/2, L) - L/2, each op rounded once
+  t = __fadd_rn(t, half);
+  if (GENERAL) {
+    t = wrap_pos(t, L);
+  } else {
+    // wrapped inputs: t in [-L/2, 3L/2]; this branch form is bit-identical to fmod-based mod
+    if (t < 0.f) t = __fadd_rn(t, L);
+    else if (t >= L) t = __fsub_rn(t, L);
+  }
+  return __fsub_rn(t, half);
+}
+
+template <bool GENERAL>
+__device__ __forceinline__ float pair_dr2(const float4& pc, const float4& pn, const NbrParams& p) {
+  float tx = min_image<GENERAL>(__fsub_rn(pc.x, pn.x), p.box[0], p.half[0]);
+  float ty = min_image<GENERAL>(__fsub_rn(pc.y, pn.y), p.box[1], p.half[1]);
+  float tz = min_image<GENERAL>(__fsub_rn(pc.z, pn.z), p.box[2], p.half[2]);
+  return __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz));
+}
+
+__device__ __forceinline__ bool pass_pred(float dr2, const NbrParams& p) {
+  if (p.flags & GAMD_NBR_LE) return __fsqrt_rn(dr2) <= p.rc;
+  return dr2 < p.rc2;
+}
+
+__device__ __forceinline__ uint32_t cell_key(float wx, float wy, float wz, int frame, const NbrParams& p) {
+  int cx = min(max((int)(wx * p.inv_cell[0]), 0), p.nc[0] - 1);
+  int cy = min(max((int)(wy * p.inv_cell[1]), 0), p.nc[1] - 1);
+  int cz = min(max((int)(wz * p.inv_cell[2]), 0), p.nc[2] - 1);
+  return (uint32_t)(frame * p.cells_per_frame + (cz * p.nc[1] + cy) * p.nc[0] + cx);
+}
+
+// ------------------------------------------------------------------------------------------
+// bin
+// ------------------------------------------------------------------------------------------
+__global__ void k_bin_f32(const float* __restrict__ pos, NbrParams p, float4* __restrict__ pos_nbr,
+                          float4* __restrict__ pos_feat, uint32_t* __restrict__ keys,
+                          uint32_t* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_atoms) return;
+  float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+  float wx = wrap_pos(x, p.box[0]), wy = wrap_pos(y, p.box[1]), wz = wrap_pos(z, p.box[2]);
+  bool raw = p.flags & GAMD_NBR_NOWRAP;
+  pos_nbr[i] = make_float4(raw ? x : wx, raw ? y : wy, raw ? z : wz, __int_as_float(i));
+  pos_feat[i] = make_float4(raw ? x : wx, raw ? y : wy, raw ? z : wz, 0.f);
+  keys[i] = cell_key(wx, wy, wz, i / p.atoms_per_frame, p);
+  vals[i] = i;
+}
+
+// engine path: fp64 state (x * scale = Angstrom).  Restates predict_forces exactly:
+//   neighbor positions  = jnp.mod(f32(pos), f32(L))            (train_network_lj.py:188, graph_utils.py:37)
+//   feature positions   = f32(np.mod(pos, L)) in float64 first  (train_network_lj.py:141-142)
+__global__ void k_bin_f64(const double* __restrict__ x, double scale, double bx, double by, double bz,
+                          NbrParams p, float4* __restrict__ pos_nbr, float4* __restrict__ pos_feat,
+                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_atoms) return;
+  double px = x[3 * i] * scale, py = x[3 * i + 1] * scale, pz = x[3 * i + 2] * scale;
+  float wx = wrap_pos((float)px, p.box[0]), wy = wrap_pos((float)py, p.box[1]), wz = wrap_pos((float)pz, p.box[2]);
+  double fx = fmod(px, bx), fy = fmod(py, by), fz = fmod(pz, bz);
+  if (fx < 0.0) fx += bx;
+  if (fy < 0.0) fy += by;
+  if (fz < 0.0) fz += bz;
+  pos_nbr[i] = make_float4(wx, wy, wz, __int_as_float(i));
+  pos_feat[i] = make_float4((float)fx, (float)fy, (float)fz, 0.f);
+  keys[i] = cell_key(wx, wy, wz, i / p.atoms_per_frame, p);
+  vals[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan (int32), n inputs -> n+1 outputs (out[n] = total)
+// ------------------------------------------------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+  // exclusive scan of one int per thread over SCAN_THREADS threads
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int ws = lane < (SCAN_THREADS / 32) ? s_warp[lane] : 0;
+    int winc = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < (SCAN_THREADS / 32)) s_warp[lane] = winc - ws;
+    if (lane == (SCAN_THREADS / 32) - 1) s_warp[SCAN_THREADS / 32] = winc;
+  }
+  __syncthreads();
+  int res = inc - v + s_warp[w];
+  total = s_warp[SCAN_THREADS / 32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void k_scan_partial(const int* __restrict__ in, int64_t n, int* __restrict__ block_sums) {
+  __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++)
+    if (base + k < n) s += in[base + k];
+  int total;
+  block_exclusive_scan(s, s_warp, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void k_scan_top(int* __restrict__ block_sums, int nb) {
+  __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+  int carry = 0;
+  for (int base = 0; base < nb; base += SCAN_THREADS) {
+    int i = base + threadIdx.x;
+    int v = i < nb ? block_sums[i] : 0;
+    int total;
+    int ex = block_exclusive_scan(v, s_warp, total);
+    if (i < nb) block_sums[i] = ex + carry;
+    carry += total;
+  }
+}
+
+__global__ void k_scan_final(const int* __restrict__ in, int* __restrict__ out, int64_t n,
+                             const int* __restrict__ block_sums, int* __restrict__ total_out) {
+  __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  int total;
+  int ex = block_exclusive_scan(s, s_warp, total) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+    if (base + k == n - 1) {
+      out[n] = ex;
+      if (total_out) *total_out = ex;
+    }
+  }
+}
+
+__global__ void k_scan_empty(int* out, int* total_out) {
+  out[0] = 0;
+  if (total_out) *total_out = 0;
+}
+
+static int scan_with_total(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, int* d_total, cudaStream_t st) {
+  if (n == 0) {
+    k_scan_empty<<<1, 1, 0, st>>>(d_out, d_total);
+    GAMD_LAUNCH_CHECK();
+    return 0;
+  }
+  int nb = ceil_div(n, SCAN_TILE);
+  int* sums = (int*)ctx->scan_tmp;
+  k_scan_partial<<<nb, SCAN_THREADS, 0, st>>>(d_in, n, sums);
+  GAMD_LAUNCH_CHECK();
+  k_scan_top<<<1, SCAN_THREADS, 0, st>>>(sums, nb);
+  GAMD_LAUNCH_CHECK();
+  k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(d_in, d_out, n, sums, d_total);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cudaStream_t st) {
+  return scan_with_total(ctx, d_in, d_out, n, nullptr, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// stable LSD radix sort of (key, value) pairs, 8 bits per pass
+// ------------------------------------------------------------------------------------------
+#define RS_THREADS 256
+#define RS_ITEMS 8
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+#define RS_WARPS (RS_THREADS / 32)
+
+__global__ void k_radix_hist(const uint32_t* __restrict__ keys, int n, int shift, int nblocks,
+                             uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  int base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    int i = base + k * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];   // digit-major
+}
+
+__global__ void k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
+                                int shift, int nblocks, const uint32_t* __restrict__ offs,
+                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  // warp w owns the contiguous sub-range [w*256, (w+1)*256) of the tile -> stable
+  __shared__ uint32_t s_cnt[RS_WARPS][256];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) s_cnt[w][d] = 0;
+  __syncwarp();
+  int base = blockIdx.x * RS_TILE + w * (RS_TILE / RS_WARPS);
+  uint32_t k[RS_ITEMS], v[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    int i = base + r * 32 + lane;
+    bool ok = i < n;
+    k[r] = ok ? keys[i] : 0xffffffffu;
+    v[r] = ok ? vals[i] : 0u;
+    uint32_t d = (k[r] >> shift) & 255u;
+    uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : 256u);
+    uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    uint32_t cur = 0;
+    if (ok) cur = s_cnt[w][d];
+    __syncwarp();
+    if (ok && before == 0) s_cnt[w][d] = cur + __popc(peers);
+    __syncwarp();
+    rank[r] = cur + before;
+  }
+  __syncthreads();
+  {  // per digit: exclusive prefix over warps + global offset
+    int d = threadIdx.x;
+    uint32_t run = offs[d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ww++) {
+      uint32_t c = s_cnt[ww][d];
+      s_cnt[ww][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    int i = base + r * 32 + lane;
+    if (i < n) {
+      uint32_t d = (k[r] >> shift) & 255u;
+      uint32_t dst = s_cnt[w][d] + rank[r];
+      keys_out[dst] = k[r];
+      vals_out[dst] = v[r];
+    }
+  }
+}
+
+// sorts ctx->keys[0]/vals[0]; returns the index (0/1) of the buffer holding the result
+static int radix_sort_pairs(gamd_ctx* ctx, int n, int key_bits, cudaStream_t st, int* result_buf) {
+  int cur = 0;
+  int nblocks = ceil_div(n, RS_TILE);
+  for (int shift = 0; shift < key_bits; shift += 8) {
+    k_radix_hist<<<nblocks, RS_THREADS, 0, st>>>(ctx->keys[cur], n, shift, nblocks, ctx->radix_hist);
+    GAMD_LAUNCH_CHECK();
+    int rc = exclusive_scan_i32(ctx, (const int*)ctx->radix_hist, (int*)ctx->radix_hist + 256 * nblocks + 8,
+                                (int64_t)256 * nblocks, st);
+    if (rc) return rc;
+    k_radix_scatter<<<nblocks, RS_THREADS, 0, st>>>(ctx->keys[cur], ctx->vals[cur], n, shift, nblocks,
+                                                    ctx->radix_hist + 256 * nblocks + 8, ctx->keys[cur ^ 1],
+                                                    ctx->vals[cur ^ 1]);
+    GAMD_LAUNCH_CHECK();
+    cur ^= 1;
+  }
+  *result_buf = cur;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// gather into cell order + cell_start table
+// ------------------------------------------------------------------------------------------
+__global__ void k_gather_sorted(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
+                                int ncells, const float4* __restrict__ pos_nbr, const float4* __restrict__ pos_feat,
+                                const float* __restrict__ feat, float4* __restrict__ pos_nbr_s,
+                                float4* __restrict__ pos_feat_s, int* __restrict__ perm,
+                                int* __restrict__ cell_start) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int i = (int)vals[s];
+  pos_nbr_s[s] = pos_nbr[i];
+  float4 pf = pos_feat[i];
+  pf.w = feat ? feat[i] : 0.f;
+  pos_feat_s[s] = pf;
+  perm[s] = i;
+  int k = (int)keys[s];
+  int kp = s > 0 ? (int)keys[s - 1] : -1;
+  for (int c = kp + 1; c <= k; c++) cell_start[c] = s;
+  if (s == n - 1)
+    for (int c = k + 1; c <= ncells; c++) cell_start[c] = n;
+}
+
+// ------------------------------------------------------------------------------------------
+// 27-cell sweep, one warp per centre
+// ------------------------------------------------------------------------------------------
+template <bool WRITE, bool GENERAL>
+__device__ __forceinline__ int sweep_range(int lo, int hi, int s, const float4& pc, const NbrParams& p,
+                                           const float4* __restrict__ pos, int lane, int base, int cap,
+                                           int* __restrict__ col, int* __restrict__ edst) {
+  int cnt = 0;
+  for (int j0 = lo; j0 < hi; j0 += 32) {
+    int j = j0 + lane;
+    bool ok = j < hi;
+    if (ok) {
+      float4 pn = pos[j];
+      ok = pass_pred(pair_dr2<GENERAL>(pc, pn, p), p);
+      if (j == s) ok = (p.flags & GAMD_NBR_SELF) != 0;
+    }
+    uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (WRITE && ok) {
+      int dst = base + cnt + __popc(m & ((1u << lane) - 1u));
+      if (dst < cap) {
+        col[dst] = j;
+        edst[dst] = s;
+      }
+    }
+    cnt += __popc(m);
+  }
+  return cnt;
+}
+
+template <bool WRITE, bool GENERAL>
+__global__ void __launch_bounds__(256) k_sweep(NbrParams p, const float4* __restrict__ pos,
+                                               const uint32_t* __restrict__ keys,
+                                               const int* __restrict__ cell_start, int* __restrict__ deg,
+                                               const int* __restrict__ row_ptr, int* __restrict__ col,
+                                               int* __restrict__ edst, int cap, int* __restrict__ err_flag) {
+  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (s >= p.n_atoms) return;
+  float4 pc = pos[s];
+  int key = (int)keys[s];
+  int frame = key / p.cells_per_frame;
+  int c = key - frame * p.cells_per_frame;
+  int cx = c % p.nc[0];
+  int cy = (c / p.nc[0]) % p.nc[1];
+  int cz = c / (p.nc[0] * p.nc[1]);
+  int base = WRITE ? row_ptr[s] : 0;
+  if (WRITE && row_ptr[s + 1] > cap) {
+    if (lane == 0) atomicOr(err_flag, 1);
+    return;
+  }
+  int cnt = 0;
+  int nz = p.nc[2] >= 3 ? 3 : 1, ny = p.nc[1] >= 3 ? 3 : 1;
+  for (int iz = 0; iz < nz; iz++) {
+    int zz = nz == 3 ? (cz + iz - 1 + p.nc[2]) % p.nc[2] : 0;
+    for (int iy = 0; iy < ny; iy++) {
+      int yy = ny == 3 ? (cy + iy - 1 + p.nc[1]) % p.nc[1] : 0;
+      int rowbase = frame * p.cells_per_frame + (zz * p.nc[1] + yy) * p.nc[0];
+      int ncx = p.nc[0];
+      if (ncx <= 3) {  // whole x-row (ncx == 3 or single-cell fallback)
+        cnt += sweep_range<WRITE, GENERAL>(cell_start[rowbase], cell_start[rowbase + ncx], s, pc, p, pos, lane,
+                                            base + cnt, cap, col, edst);
+      } else if (cx == 0) {
+        cnt += sweep_range<WRITE, GENERAL>(cell_start[rowbase + ncx - 1], cell_start[rowbase + ncx], s, pc, p, pos,
+                                            lane, base + cnt, cap, col, edst);
+        cnt += sweep_range<WRITE, GENERAL>(cell_start[rowbase], cell_start[rowbase + 2], s, pc, p, pos, lane,
+                                            base + cnt, cap, col, edst);
+      } else if (cx == ncx - 1) {
+        cnt += sweep_range<WRITE, GENERAL>(cell_start[rowbase + cx - 1], cell_start[rowbase + ncx], s, pc, p, pos,
+                                            lane, base + cnt, cap, col, edst);
+        cnt += sweep_range<WRITE, GENERAL>(cell_start[rowbase], cell_start[rowbase + 1], s, pc, p, pos, lane,
+                                            base + cnt, cap, col, edst);
+      } else {
+        cnt += sweep_range<WRITE, GENERAL>(cell_start[rowbase + cx - 1], cell_start[rowbase + cx + 2], s, pc, p, pos,
+                                            lane, base + cnt, cap, col, edst);
+      }
+    }
+  }
+  if (!WRITE && lane == 0) deg[s] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+int nbr_setup_params(gamd_ctx* ctx, int64_t n_atoms, int n_frames, const float box[3], float rc, int flags,
+                     NbrParams* p) {
+  if (n_atoms <= 0 || n_frames <= 0 || n_atoms % n_frames != 0) {
+    ctx->err = "n_atoms must be a positive multiple of n_frames";
+    return GAMD_EINVAL;
+  }
+  if (!(rc > 0.f) || !(box[0] > 0.f) || !(box[1] > 0.f) || !(box[2] > 0.f)) {
+    ctx->err = "box and cutoff must be positive";
+    return GAMD_EINVAL;
+  }
+  if (n_atoms > ctx->cap_atoms) {
+    ctx->err = "n_atoms exceeds reserved capacity; call gamd_reserve";
+    return GAMD_ECAPACITY;
+  }
+  int64_t cells = 1;
+  for (int d = 0; d < 3; d++) {
+    p->box[d] = box[d];
+    p->half[d] = box[d] * 0.5f;
+    // cell edge >= rc*(1+1e-3): a pair two cells apart can never pass the fp32 test by rounding
+    int nc = (int)floor((double)box[d] / ((double)rc * 1.001));
+    if (nc < 3) nc = 1;  // fewer than 3 cells: treat the axis as one cell (brute force along it)
+    p->nc[d] = nc;
+    p->inv_cell[d] = (float)((double)nc / (double)box[d]);
+    cells *= nc;
+  }
+  // keep the cell table small relative to the atom count (huge sparse boxes)
+  while (cells * n_frames > 4 * n_atoms + 64 && cells > 27) {
+    int dmax = 0;
+    for (int d = 1; d < 3; d++)
+      if (p->nc[d] > p->nc[dmax]) dmax = d;
+    if (p->nc[dmax] <= 3) break;
+    cells /= p->nc[dmax];
+    p->nc[dmax]--;
+    cells *= p->nc[dmax];
+    p->inv_cell[dmax] = (float)((double)p->nc[dmax] / (double)box[dmax]);
+  }
+  if (cells * n_frames + 1 > ctx->cap_cells) {
+    ctx->err = "cell table exceeds reserved capacity";
+    return GAMD_ECAPACITY;
+  }
+  p->cells_per_frame = (int)cells;
+  p->n_atoms = (int)n_atoms;
+  p->atoms_per_frame = (int)(n_atoms / n_frames);
+  p->n_frames = n_frames;
+  p->rc = rc;
+  // python: `dr_2 < cutoff ** 2` - the square is taken in double, then rounded to fp32
+  p->rc2 = (float)((double)rc * (double)rc);
+  p->flags = flags;
+  return 0;
+}
+
+int nbr_bin_f32(gamd_ctx* ctx, const float* d_pos, const NbrParams& p, cudaStream_t st) {
+  k_bin_f32<<<ceil_div(p.n_atoms, 256), 256, 0, st>>>(d_pos, p, ctx->pos_nbr, ctx->pos_feat, ctx->keys[0],
+                                                      ctx->vals[0]);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int nbr_bin_f64(gamd_ctx* ctx, const double* d_x, double scale, const double* box64, const NbrParams& p,
+                cudaStream_t st) {
+  k_bin_f64<<<ceil_div(p.n_atoms, 256), 256, 0, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, ctx->pos_nbr,
+                                                      ctx->pos_feat, ctx->keys[0], ctx->vals[0]);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, cudaStream_t st) {
+  int n = p.n_atoms;
+  int64_t ncells = (int64_t)p.cells_per_frame * p.n_frames;
+  int bits = 1;
+  while (((int64_t)1 << bits) < ncells) bits++;
+  int buf = 0;
+  int rc = 0;
+  if (ncells > 1) {
+    rc = radix_sort_pairs(ctx, n, bits, st, &buf);
+    if (rc) return rc;
+  }
+  k_gather_sorted<<<ceil_div(n, 256), 256, 0, st>>>(ctx->keys[buf], ctx->vals[buf], n, (int)ncells, ctx->pos_nbr,
+                                                    ctx->pos_feat, d_feat, ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm,
+                                                    ctx->cell_start);
+  GAMD_LAUNCH_CHECK();
+  int cap = (int)ctx->cap_edges;
+  int blocks = ceil_div((int64_t)n * 32, 256);
+  bool general = (p.flags & GAMD_NBR_NOWRAP) != 0;
+  if (general)
+    k_sweep<false, true><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg, nullptr,
+                                                 nullptr, nullptr, cap, ctx->err_flag);
+  else
+    k_sweep<false, false><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg,
+                                                  nullptr, nullptr, nullptr, cap, ctx->err_flag);
+  GAMD_LAUNCH_CHECK();
+  rc = scan_with_total(ctx, ctx->deg, ctx->row_ptr, n, ctx->n_edges, st);
+  if (rc) return rc;
+  if (general)
+    k_sweep<true, true><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg,
+                                                ctx->row_ptr, ctx->col_idx, ctx->edge_dst, cap, ctx->err_flag);
+  else
+    k_sweep<true, false><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg,
+                                                 ctx->row_ptr, ctx->col_idx, ctx->edge_dst, cap, ctx->err_flag);
+  GAMD_LAUNCH_CHECK();
+  ctx->last_nbr = p;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// export: CSR in sorted space -> COO in caller ids (centre-major, neighbour ascending)
+// ------------------------------------------------------------------------------------------
+__global__ void k_deg_to_orig(const int* __restrict__ deg, const int* __restrict__ perm, int n, int* __restrict__ deg_o) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) deg_o[perm[s]] = deg[s];
+}
+
+__global__ void k_export_rows(NbrParams p, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                              const int* __restrict__ perm, const int* __restrict__ row_ptr_o,
+                              const float4* __restrict__ pos_orig, int64_t* __restrict__ out, int64_t cap,
+                              float* __restrict__ dist, float* __restrict__ norm) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.n_atoms) return;
+  int i = perm[s];
+  int b = row_ptr_o[i], d = row_ptr[s + 1] - row_ptr[s];
+  if ((int64_t)b + d > cap) return;
+  int64_t* nb = out + cap + b;
+  for (int k = 0; k < d; k++) {  // insertion sort by caller id
+    int64_t j = perm[col[row_ptr[s] + k]];
+    int q = k;
+    while (q > 0 && nb[q - 1] > j) {
+      nb[q] = nb[q - 1];
+      q--;
+    }
+    nb[q] = j;
+  }
+  float4 pc = pos_orig[i];
+  for (int k = 0; k < d; k++) {
+    out[b + k] = i;
+    if (dist || norm) {
+      float4 pn = pos_orig[nb[k]];
+      float tx = min_image<true>(__fsub_rn(pc.x, pn.x), p.box[0], p.half[0]);
+      float ty = min_image<true>(__fsub_rn(pc.y, pn.y), p.box[1], p.half[1]);
+      float tz = min_image<true>(__fsub_rn(pc.z, pn.z), p.box[2], p.half[2]);
+      if (dist) {
+        dist[3 * (b + k)] = tx;
+        dist[3 * (b + k) + 1] = ty;
+        dist[3 * (b + k) + 2] = tz;
+      }
+      if (norm) norm[b + k] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz)));
+    }
+  }
+}
+
+int nbr_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float* d_dist, float* d_norm, cudaStream_t st) {
+  const NbrParams& p = ctx->last_nbr;
+  int n = p.n_atoms;
+  if (n <= 0) {
+    ctx->err = "gamd_neighbor_export before gamd_neighbor_build";
+    return GAMD_ESTATE;
+  }
+  k_deg_to_orig<<<ceil_div(n, 256), 256, 0, st>>>(ctx->deg, ctx->perm, n, ctx->deg_o);
+  GAMD_LAUNCH_CHECK();
+  int rc = exclusive_scan_i32(ctx, ctx->deg_o, ctx->row_ptr_o, n, st);
+  if (rc) return rc;
+  k_export_rows<<<ceil_div(n, 128), 128, 0, st>>>(p, ctx->row_ptr, ctx->col_idx, ctx->perm, ctx->row_ptr_o,
+                                                  ctx->pos_nbr, d_edge_idx, cap, d_dist, d_norm);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// explicit edge list (sorted by centre) -> CSR, caller index space
+// ------------------------------------------------------------------------------------------
+__global__ void k_coo_to_csr(const int64_t* __restrict__ center, const int64_t* __restrict__ neigh, int64_t n_edges,
+                             int n_atoms, int* __restrict__ row_ptr, int* __restrict__ col, int* __restrict__ edst,
+                             int* __restrict__ n_edges_dev, int* __restrict__ err_flag) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0) *n_edges_dev = (int)n_edges;
+  if (e >= n_edges) return;
+  int c = (int)center[e];
+  int cp = e > 0 ? (int)center[e - 1] : -1;
+  if (c < cp || c < 0 || c >= n_atoms || neigh[e] < 0 || neigh[e] >= n_atoms) {
+    atomicOr(err_flag, 2);  // not sorted by centre / id out of range
+    return;
+  }
+  col[e] = (int)neigh[e];
+  edst[e] = c;
+  for (int r = cp + 1; r <= c; r++) row_ptr[r] = (int)e;
+  if (e == n_edges - 1)
+    for (int r = c + 1; r <= n_atoms; r++) row_ptr[r] = (int)n_edges;
+}
+
+int csr_from_sorted_coo(gamd_ctx* ctx, const int64_t* d_center, const int64_t* d_neigh, int64_t n_atoms,
+                        int64_t n_edges, cudaStream_t st) {
+  if (n_edges > ctx->cap_edges || n_atoms > ctx->cap_atoms) {
+    ctx->err = "edge list exceeds reserved capacity; call gamd_reserve";
+    return GAMD_ECAPACITY;
+  }
+  if (n_edges == 0) {
+    GAMD_CUDA(cudaMemsetAsync(ctx->row_ptr, 0, sizeof(int) * (n_atoms + 1), st));
+    GAMD_CUDA(cudaMemsetAsync(ctx->n_edges, 0, sizeof(int), st));
+    return 0;
+  }
+  k_coo_to_csr<<<ceil_div(n_edges, 256), 256, 0, st>>>(d_center, d_neigh, n_edges, (int)n_atoms, ctx->row_ptr,
+                                                       ctx->col_idx, ctx->edge_dst, ctx->n_edges, ctx->err_flag);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}

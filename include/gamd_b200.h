@@ -1,0 +1,190 @@
+/* gamd_b200 - C ABI of the B200-native GAMD hot path
+ *
+ * positions + box --> periodic neighbor search --> MDNet message passing --> per-atom
+ * forces --> velocity-Verlet update.
+ *
+ * The reference (BaratiLab/GAMD) has no FFI: its boundary for this path is four Python call
+ * surfaces.  Each entry point below names the reference interface it replaces (paths are
+ * relative to the reference tree, file:line).  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative GAMD_E* code otherwise;
+ *     gamd_last_error(ctx) returns a human-readable message.  No C++ exception crosses.
+ *   - pointers named d_* are caller-owned DEVICE pointers (e.g. torch tensors); h_* are HOST
+ *     pointers.  The library never frees caller memory.  Its own scratch memory is sized by
+ *     gamd_reserve() and lives until gamd_destroy().
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (void*, 0 = default
+ *     stream); nothing synchronises the host unless the function name ends in _host or
+ *     the comment says so.
+ *   - one ctx per device and per host thread; distinct ctxs are independent.
+ *   - sizes the kernels are built for in this round: encoding_size = hidden_dim =
+ *     edge_embedding_dim = 128 (every LJ / TIP3P / TIP4P config the reference ships,
+ *     code/LJ/test_script/test_nosehoover.py:66-69); other widths return GAMD_EUNSUPPORTED.
+ */
+#ifndef GAMD_B200_H
+#define GAMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gamd_ctx gamd_ctx;
+
+enum {
+  GAMD_OK = 0,
+  GAMD_EINVAL = -1,        /* bad argument */
+  GAMD_ECUDA = -2,         /* CUDA runtime error (text in gamd_last_error) */
+  GAMD_EUNSUPPORTED = -3,  /* model shape / option not built */
+  GAMD_ECAPACITY = -4,     /* edge or atom capacity exceeded: the analogue of jax-md's
+                              did_buffer_overflow (code/graph_utils.py:41); call gamd_reserve
+                              with a larger capacity and retry */
+  GAMD_ESTATE = -5,        /* call order violated (e.g. weights not finalized) */
+  GAMD_ENOGPU = -6         /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/* neighbor predicate flags */
+enum {
+  GAMD_NBR_LT = 0,        /* dr2 <  rc*rc     (code/graph_utils.py:59, jax-md path)      */
+  GAMD_NBR_LE = 1,        /* |dr| <= rc       (code/md_module.py:111, torch brute force) */
+  GAMD_NBR_SELF = 2,      /* keep the i==i pair (mask_self=False, code/graph_utils.py:25) */
+  GAMD_NBR_NOWRAP = 4     /* predicate uses the raw positions (md_module.get_neighbor
+                             applies no jnp.mod); cells are still assigned from wrapped ones */
+};
+
+/* model kinds: which reference nn.Module the weights belong to */
+enum {
+  GAMD_MODEL_LJ = 0,      /* SimpleMDNetNew        code/nn_module.py:561-685 */
+  GAMD_MODEL_WATER = 1,   /* WaterMDNetNew         code/nn_module.py:410-558 */
+  GAMD_MODEL_DYNBOX = 2   /* WaterMDDynamicBoxNet  code/nn_module.py:266-407 */
+};
+
+/* arithmetic of the edge-sized GEMMs */
+enum {
+  GAMD_PREC_FP32 = 0,     /* CUDA-core FFMA, fp32 everywhere (parity anchor)            */
+  GAMD_PREC_BF16X3 = 1,   /* tcgen05, 3-pass split-bf16, fp32 accumulate ("exact" mode) */
+  GAMD_PREC_BF16 = 2      /* tcgen05, single-pass bf16 operands ("fast" mode)           */
+};
+
+typedef struct {
+  int32_t kind;            /* GAMD_MODEL_* */
+  int32_t encoding_size;   /* D  */
+  int32_t hidden_dim;      /* H  */
+  int32_t edge_dim;        /* De */
+  int32_t conv_layer;      /* L  */
+  int32_t in_feats;        /* node_encoder input width (water: 1), 0 for LJ */
+  int32_t use_bond;        /* 1: last edge feature is the bond flag (45 inputs) */
+  int32_t expand_edge;     /* 1: 40-centre RBF expansion */
+  int32_t precision;       /* GAMD_PREC_* */
+} gamd_model_desc;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* replaces: model construction, code/LJ/train_network_lj.py:68-88 (build_model) */
+int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out);
+int gamd_destroy(gamd_ctx* ctx);
+const char* gamd_last_error(const gamd_ctx* ctx);   /* ctx may be NULL: last create error */
+const char* gamd_version(void);
+
+/* scratch for up to max_atoms nodes and max_edges directed edges (device allocations
+ * happen here, never on the hot path).  May be called again to grow. */
+int gamd_reserve(gamd_ctx* ctx, int64_t max_atoms, int64_t max_edges);
+
+/* ---- weights ------------------------------------------------------------------------- */
+/* replaces: model.load_state_dict / load_from_checkpoint, code/LJ/train_network_lj.py:85-87,
+ * code/LJ/test_script/test_nosehoover.py:77.  `name` is the reference state-dict key
+ * (SURVEY.md section 8a note 9), `h_data` the fp32 tensor in torch's row-major layout. */
+int gamd_load_weight(gamd_ctx* ctx, const char* name, const float* h_data, int64_t n);
+/* replaces: load_training_stats (scaler.npz), code/LJ/train_network_lj.py:119-123 */
+int gamd_set_scaler(gamd_ctx* ctx, double mean, double var);
+/* bond list for the water model's bond flag: nb pairs (i,j) of frame-local atom ids,
+ * made symmetric internally. replaces: build_bond_graph, code/nn_module.py:529-534 */
+int gamd_set_bonds(gamd_ctx* ctx, const int64_t* h_bonds, int64_t nb, int64_t n_atoms_per_frame);
+/* checks that every tensor arrived, builds the transposed / split device copies */
+int gamd_finalize_weights(gamd_ctx* ctx);
+
+/* ---- stage 1: neighbor search ---------------------------------------------------------- */
+/* replaces: NeighborSearcher.init_new_neighbor_lst / update_neighbor_lst
+ *           (code/graph_utils.py:29-44), nbrlst_to_edge_mask (code/graph_utils.py:51-61),
+ *           search_for_neighbor + get_edge_idx (code/LJ/train_network_lj.py:166-199) and
+ *           get_neighbor (code/md_module.py:93-126, flags LE|NOWRAP, no SELF).
+ * d_pos: fp32 [n_atoms,3] Angstrom, any image; h_box is the box in double (the reference's
+ * python float); the fp32 box used by the kernels is (float)h_box[d], as jnp.array does.  n_frames independent frames of
+ * n_atoms/n_frames atoms each share the box (block-diagonal batch, code/nn_module.py:655-661).
+ * Builds, inside ctx, a receiver-sorted CSR in cell-sorted index space. */
+int gamd_neighbor_build(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, int32_t n_frames,
+                        const double h_box[3], float cutoff, int32_t flags, void* stream);
+/* number of edges of the last build; synchronises `stream`. */
+int gamd_neighbor_count_host(gamd_ctx* ctx, int64_t* n_edges, void* stream);
+/* COO export in the reference's format: int64 [2,cap] row 0 centre, row 1 neighbour, caller
+ * atom ids, centre-major, neighbour ascending (code/LJ/train_network_lj.py:182-185).
+ * d_dist / d_norm (optional, may be NULL): fp32 [cap,3] min-image pos[centre]-pos[neigh] and
+ * its norm, as get_neighbor returns (code/md_module.py:119-121). */
+int gamd_neighbor_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float* d_dist,
+                         float* d_norm, void* stream);
+
+/* ---- stage 2: MDNet forward on an explicit edge list ----------------------------------- */
+/* replaces: SimpleMDNetNew.forward (code/nn_module.py:672-685), WaterMDNetNew.forward
+ *           (:545-558).  d_pos fp32 [n,3] already wrapped by the caller (as
+ *           train_network_lj.py:141 does), d_center / d_neigh int64 [n_edges] sorted by
+ *           centre (the order get_edge_idx produces), d_feat fp32 [n] node type feature
+ *           (water) or NULL (LJ), frames are concatenated with frame-local ids already
+ *           offset.  d_out fp32 [n,3] normalised force. */
+int gamd_model_forward(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, int32_t n_frames,
+                       const double h_box[3], const int64_t* d_center, const int64_t* d_neigh,
+                       int64_t n_edges, const float* d_feat, float* d_out, void* stream);
+
+/* ---- stage 1+2 fused: positions -> forces ---------------------------------------------- */
+/* replaces: ParticleNetLightning.predict_forces (code/LJ/train_network_lj.py:133-157,
+ *           code/water/train_network_tip3p.py:142-159): neighbor search on fp32(pos), model
+ *           on fp32(mod(pos, L)), de-normalisation in fp64.
+ * d_pos fp64 [n,3] Angstrom; d_force fp64 [n,3] kJ/mol/nm. */
+int gamd_compute_forces(gamd_ctx* ctx, const double* d_pos, int64_t n_atoms, int32_t n_frames,
+                        const double h_box[3], float cutoff, const float* d_feat, double* d_force,
+                        void* stream);
+/* same through HOST buffers (H2D + D2H inside, synchronous) - the predict_forces call shape */
+int gamd_compute_forces_host(gamd_ctx* ctx, const double* h_pos, int64_t n_atoms, int32_t n_frames,
+                             const double h_box[3], float cutoff, const float* h_feat,
+                             double* h_force);
+
+/* ---- stage 3: integrator hook ------------------------------------------------------------ */
+/* replaces: HackNoseHooverIntegrator step body with chain_length=0
+ *           (code/hack_integrator.py:271-277: v+=0.5*dt*force_last/m; x+=dt*v) */
+int gamd_vv_first_half(gamd_ctx* ctx, double* d_x, double* d_v, const double* d_f,
+                       const double* d_mass, int64_t n_atoms, double dt, void* stream);
+/* replaces: HackHalfVelocityIntegrator (code/hack_integrator.py:171-178:
+ *           v+=(dt/2)*gnn_force/m) */
+int gamd_vv_second_half(gamd_ctx* ctx, double* d_v, const double* d_f, const double* d_mass,
+                        int64_t n_atoms, double dt, void* stream);
+
+/* ---- whole MD step, device resident ------------------------------------------------------ */
+/* replaces: the driver loop body code/LJ/test_script/test_nosehoover.py:100-118 (NVE program):
+ *   first half-kick + drift with d_f, forces at the new positions, second half-kick.
+ * d_x (nm), d_v (nm/ps), d_f (kJ/mol/nm, holds F(x) on entry and F(x') on exit) fp64 [n,3],
+ * d_mass fp64 [n] (Da).  Runs n_steps steps; no host synchronisation.
+ * d_ke (optional): fp64 [n_steps] total kinetic energy after each step (kJ/mol). */
+int gamd_md_run(gamd_ctx* ctx, double* d_x, double* d_v, double* d_f, const double* d_mass,
+                int64_t n_atoms, int32_t n_frames, const double h_box[3], float cutoff,
+                const float* d_feat, double dt, int32_t n_steps, double* d_ke, void* stream);
+/* one step through HOST buffers (H2D of x,v,f + step + D2H of x,v,f), synchronous */
+int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, const double* h_mass,
+                      int64_t n_atoms, int32_t n_frames, const double h_box[3], float cutoff,
+                      const float* h_feat, double dt);
+
+/* synchronises `stream` and reports errors raised asynchronously on the device since the
+ * last check (GAMD_ECAPACITY: edge capacity exceeded; GAMD_EINVAL: edge list not sorted by
+ * centre or ids out of range).  The *_host entry points call it themselves. */
+int gamd_check_async_errors(gamd_ctx* ctx, void* stream);
+
+/* ---- introspection (tests, profiling) ---------------------------------------------------- */
+/* device pointers into ctx scratch, valid until the next gamd_reserve: names
+ * "row_ptr","col_idx","edge_dst","perm","n_edges","pos_sorted","e_emb","h","agg","pred". */
+int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_bytes);
+/* number of kernel launches issued by this ctx since creation */
+int64_t gamd_launch_count(const gamd_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAMD_B200_H */
