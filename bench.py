@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the GNN-MD hot path (BASELINE.json metric: atom-steps/s of GNN-force MD).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lj1m|lj258|tip3p774|lj32k]
+                    [--impl ours|reference] [--precision fp32|bf16x3|bf16]
+
+A "step" is one whole MD step - first half-kick + drift, periodic neighbor search, MDNet
+force prediction (edge encoder + 4 message-passing layers + decoder), second half-kick - on a
+synthetic random-init-weight system.  Default workload: the 1 000 000-atom LJ box of
+BASELINE.json configs[3] (the configuration the metric's "1/2/4/8 B200" is quoted on; it fits
+one GPU).  Prints ONE JSON line (rank 0).
+
+  value     atom-steps/s with the state resident in HBM (device timed, CUDA events, max over ranks)
+  e2e       the same through the host-buffer call (MDEngine.step_host -> gamd_md_step_host):
+            H2D of x, v, f, masses and D2H of x, v, f inside the timed region, pinned buffers
+  roofline  the dominant kernel (message-passing edge chain) against the measured tensor peak
+  cpu_baseline  the CPU oracle (port of the reference path) on a bounded sample, rank 0, N=1
+
+`--impl reference` times that CPU oracle as the reference arm (the reference is Python and
+needs DGL/jax-md/OpenMM, none installable here; oracle/ restates it and is pinned to the
+reference's nn_module.py by golden vectors - see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, n_side or None, description)
+    "lj1m": dict(kind="lj", n_side=100, desc="LJ box 1,000,000 atoms (configs[3]), L=428.4 A, rc=7.5 A"),
+    "lj32k": dict(kind="lj", n_side=32, desc="LJ box 32,768 atoms, same density/cutoff"),
+    "lj258": dict(kind="lj", n_side=None, desc="LJ argon 258 atoms (configs[0] fixture)"),
+    "tip3p774": dict(kind="water", n_side=None, desc="TIP3P 258 molecules / 774 atoms (configs[1] fixture)"),
+}
+FIX = os.path.join(ROOT, "tests", "golden", "fixtures")
+DT = 0.002  # ps (test_nosehoover.py:29)
+
+
+def build_system(name, seed=42):
+    """positions (A, f64), box (A), cutoff, masses, scaler file, kind"""
+    from gamd_b200.engine import synthetic_lj_box
+    w = WORKLOADS[name]
+    if name == "lj258":
+        pos = np.load(os.path.join(FIX, "lj_init_pos.npy")).astype(np.float64)
+        return pos, 27.27, 7.5, np.full(len(pos), 39.9), "scaler_lj.npz", "lj", 100.0
+    if name == "tip3p774":
+        pos = np.load(os.path.join(FIX, "water_init_pos.npy")).astype(np.float64)
+        m = np.tile([15.999, 1.008, 1.008], len(pos) // 3)
+        return pos, 20.0, 4.2, m, "scaler_tip3p.npz", "water", 300.0
+    pos, L = synthetic_lj_box(w["n_side"], seed=seed)
+    return pos, L, 7.5, np.full(len(pos), 39.9), "scaler_lj.npz", "lj", 100.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def oracle_steps(name, steps, warmup, threads):
+    """time the CPU oracle (port of the reference path) on `name`; returns (atom-steps/s, n, s/step)"""
+    import torch
+    from gamd_b200.weights import random_state_dict, water_bonds
+    from oracle import md as omd
+    from oracle import integrator as oint
+    torch.set_num_threads(threads)
+    pos, box, rc, m, scaler, kind, temp = build_system(name)
+    s = np.load(os.path.join(FIX, scaler))
+    sd = random_state_dict(0, kind=kind)
+    if kind == "water":
+        feat = torch.zeros(len(pos), 1)
+        feat[::3] = 1.0
+        ff = omd.OracleForceField(sd, kind, box, rc, s["mean"], s["var"], bond=water_bonds(len(pos) // 3), feat=feat)
+    else:
+        ff = omd.OracleForceField(sd, kind, box, rc, s["mean"], s["var"])
+    x = pos / 10.0
+    v = omd.maxwell_boltzmann(len(pos), m, temp, 1234)
+    f = ff.predict_forces(x * 10.0)
+    t0 = None
+    for t in range(warmup + steps):
+        if t == warmup:
+            t0 = time.perf_counter()
+        x, v = oint.vv_first_half(x, v, f, m, DT)
+        f = ff.predict_forces(x * 10.0)
+        v = oint.vv_second_half(v, f, m, DT)
+    el = time.perf_counter() - t0
+    return len(pos) * steps / el, len(pos), el / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = "lj32k" if args.workload == "lj1m" else args.workload
+    steps = max(1, min(args.steps, 3)) if sample == "lj32k" else args.steps
+    warm = min(args.warmup, 1) if sample == "lj32k" else args.warmup
+    val, n, sps = oracle_steps(sample, steps, warm, threads)
+    desc = f"{WORKLOADS[sample]['desc']}: {steps} NVE steps of the CPU oracle (torch CPU fp32 + numpy), {threads} threads"
+    line = {
+        "impl": "reference", "metric": "atom-steps/s of GNN-force MD", "value": val, "unit": "atom-steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": args.workload, "sample": sample, "atoms": n, "model": "MDNet 128/128/128 x4 random-init"},
+        "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gamd_b200 import _capi
+    from gamd_b200.engine import MDEngine, maxwell_boltzmann
+    from gamd_b200.weights import random_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    prec = {"fp32": _capi.PREC_FP32, "bf16x3": _capi.PREC_BF16X3, "bf16": _capi.PREC_BF16}[args.precision]
+
+    # every rank runs its own replica of the workload (no collective on the data path)
+    pos, box, rc, m, scaler, kind, temp = build_system(args.workload, seed=42 + rank)
+    n = len(pos)
+    s = np.load(os.path.join(FIX, scaler))
+    sd = random_state_dict(0, kind=kind)
+    eng = MDEngine(kind, sd, box, rc, m, s["mean"], s["var"], precision=prec, device=local)
+    eng.set_state(pos / 10.0, maxwell_boltzmann(m, temp, 1234 + rank))
+    n_edges = eng.ctx.neighbor_count()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ----
+    eng.step(args.warmup, DT)
+    eng.ctx.check_async_errors()
+    eng.ctx.profile_enable(True)
+    for st in ("neighbor", "edge_encode", "mp_edge", "node_update", "integrate"):
+        eng.ctx.profile_read(st)
+    launches0 = eng.ctx.launch_count
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.step(args.steps, DT)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    eng.ctx.check_async_errors()
+    stages = {st: eng.ctx.profile_read(st) for st in ("neighbor", "edge_encode", "mp_edge", "node_update", "integrate")}
+    eng.ctx.profile_enable(False)
+
+    # ---- end-to-end arm: host buffers, pinned, copies inside the timed region ----
+    xh = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    vh = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    fh = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    xh.copy_(eng.x.cpu()); vh.copy_(eng.v.cpu()); fh.copy_(eng.f.cpu())
+    xn, vn, fn = xh.numpy(), vh.numpy(), fh.numpy()
+    e2e_steps = max(1, min(args.steps, 5))
+    eng.step_host(xn, vn, fn, DT)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.step_host(xn, vn, fn, DT)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = 3 * n * 24 + n * 8 + (n * 4 if kind == "water" else 0)
+    d2h = 3 * n * 24
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tensor_peak, peak_src = peaks()
+    mp_ms, mp_cnt = stages["mp_edge"]
+    mp_avg_s = mp_ms / max(mp_cnt, 1) * 1e-3
+    flop_per_launch = 131072.0 * n_edges            # 4 x (128x128) mat-vec per edge
+    achieved = flop_per_launch / mp_avg_s / 1e12 if mp_avg_s > 0 else 0.0
+    value = world * n * args.steps / (ms * 1e-3)
+    e2e_val = world * n * e2e_steps / (e2e_ms * 1e-3)
+    line = {
+        "metric": "atom-steps/s of GNN-force MD", "value": value, "unit": "atom-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (fp32 accumulate)",
+                                                          "bf16": "bf16 (fp32 accumulate)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "atoms_per_gpu": n,
+                   "edges_per_gpu": n_edges, "model": "MDNet 128/128/128 x4 layers, random-init (numpy PCG64 seed 0)",
+                   "parallelism": "replicas" if world > 1 else "single", "precision": args.precision,
+                   "l2": "working set (edge embeddings %.1f GB) is larger than L2" % (n_edges * 512 / 1e9)
+                   if n_edges * 512 > 2e8 else "working set fits L2 (latency-bound system)"},
+        "edges_per_s_per_layer": n_edges / mp_avg_s if mp_avg_s > 0 else None,
+        "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+        "roofline": {"bound": "tensor", "kernel": "k_mp_edge (message-passing edge chain + segmented reduce)",
+                     "achieved": achieved, "peak": tensor_peak / 1.0, "unit": "TFLOP/s",
+                     "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src + " bf16 sustained",
+                     "hbm_frac": ((516.0 * n_edges + 1028.0 * n) / mp_avg_s / 1e9 / hbm_peak) if mp_avg_s > 0 else None},
+        "e2e": {"value": e2e_val, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "MDEngine.step_host -> gamd_md_step_host (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = "lj32k" if args.workload == "lj1m" else args.workload
+        k = 2 if sample == "lj32k" else 20
+        val, nn, sps = oracle_steps(sample, k, 1, threads)
+        line["cpu_baseline"] = {"value": val, "unit": "atom-steps/s", "cores": threads, "kind": "port",
+                                "sample": f"{WORKLOADS[sample]['desc']}: {k} NVE steps of the CPU oracle "
+                                          f"(torch CPU fp32 + numpy), {sps:.2f} s/step"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="lj1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

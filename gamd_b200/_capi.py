@@ -62,6 +62,8 @@ SIGNATURES = {
     "gamd_check_async_errors": (c_int32, [c_void_p, c_void_p]),
     "gamd_debug_ptr": (c_int32, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
     "gamd_launch_count": (c_int64, [c_void_p]),
+    "gamd_profile_enable": (c_int32, [c_void_p, c_int32]),
+    "gamd_profile_read": (c_int32, [c_void_p, c_char_p, POINTER(c_double), POINTER(c_int64)]),
 }
 
 _lib = None
@@ -241,6 +243,14 @@ class Context:
             __cuda_array_interface__ = iface
         t = torch.as_tensor(_W(), device=torch.device("cuda", self.device))
         return t.view(dtype).view(*shape).clone()
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.gamd_profile_enable(self._h, int(on)))
+
+    def profile_read(self, stage):
+        ms, cnt = c_double(), c_int64()
+        self._check(self.lib.gamd_profile_read(self._h, stage.encode(), ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms.value, cnt.value
 
     @property
     def launch_count(self):

@@ -137,12 +137,25 @@ int positions_to_forces(gamd_ctx* ctx, const double* d_x, double scale, int64_t 
   NbrParams p;
   int rc = nbr_setup_params(ctx, n, n_frames, boxf, cutoff, GAMD_NBR_LT | GAMD_NBR_SELF, &p);
   if (rc) return rc;
+  prof_mark(ctx, "neighbor", st);
   if ((rc = nbr_bin_f64(ctx, d_x, scale, box, p, st))) return rc;
   if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
+  prof_mark(ctx, "neighbor", st);
   return model_forward_fp32(ctx, ctx->pos_feat_s, nullptr, ctx->perm, n, p.atoms_per_frame, boxf, st);
 }
 
 }  // namespace
+
+void prof_mark(gamd_ctx* ctx, const char* stage, cudaStream_t st) {
+  if (!ctx->prof_on) return;
+  auto& p = ctx->prof[stage];
+  if (p.used == p.ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    p.ev.push_back(e);
+  }
+  cudaEventRecord(p.ev[p.used++], st);
+}
 
 int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st) {
   k_pack_pos_feat<<<ceil_div(n, 256), 256, 0, st>>>(d_pos, d_feat, n, out);
@@ -596,5 +609,30 @@ int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_byt
 }
 
 int64_t gamd_launch_count(const gamd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gamd_profile_enable(gamd_ctx* ctx, int32_t on) {
+  if (!ctx) return GAMD_EINVAL;
+  ctx->prof_on = on != 0;
+  return 0;
+}
+
+int gamd_profile_read(gamd_ctx* ctx, const char* stage, double* total_ms, int64_t* launches) {
+  if (!ctx || !stage) return GAMD_EINVAL;
+  GAMD_CUDA(cudaDeviceSynchronize());
+  auto& p = ctx->prof[stage];
+  for (size_t i = 0; i + 1 < p.used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]) == cudaSuccess) {
+      p.total_ms += ms;
+      p.launches++;
+    }
+  }
+  p.used = 0;
+  if (total_ms) *total_ms = p.total_ms;
+  if (launches) *launches = p.launches;
+  p.total_ms = 0.0;
+  p.launches = 0;
+  return 0;
+}
 
 }  // extern "C"

@@ -88,7 +88,19 @@ struct gamd_ctx {
   size_t pinned_bytes = 0;
   NbrParams last_nbr{};
   int sm_count = 148;
+
+  // optional per-stage CUDA-event timers (gamd_profile_enable / gamd_profile_read)
+  struct StageProf {
+    std::vector<cudaEvent_t> ev;   // begin/end pairs
+    size_t used = 0;
+    double total_ms = 0.0;
+    int64_t launches = 0;
+  };
+  std::map<std::string, StageProf> prof;
+  bool prof_on = false;
 };
+
+void prof_mark(gamd_ctx* ctx, const char* stage, cudaStream_t st);   // call before and after the stage
 
 #define GAMD_CUDA(call)                                                                  \
   do {                                                                                   \

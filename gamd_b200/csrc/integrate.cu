@@ -67,8 +67,10 @@ __global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __re
 
 int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt,
                      cudaStream_t st) {
+  prof_mark(ctx, "integrate", st);
   k_vv_first<<<ceil_div(n, 256), 256, 0, st>>>(x, v, f, mass, n, dt);
   GAMD_LAUNCH_CHECK();
+  prof_mark(ctx, "integrate", st);
   return 0;
 }
 
@@ -82,8 +84,10 @@ int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* m
 int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt,
                          int64_t n, double* ke_out, cudaStream_t st) {
   if (ke_out) GAMD_CUDA(cudaMemsetAsync(ke_out, 0, sizeof(double), st));
+  prof_mark(ctx, "integrate", st);
   k_denorm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(ctx->pred, perm, n, sqrt(ctx->scaler_var), ctx->scaler_mean,
                                                      f_out, v, mass, dt, ke_out);
   GAMD_LAUNCH_CHECK();
+  prof_mark(ctx, "integrate", st);
   return 0;
 }

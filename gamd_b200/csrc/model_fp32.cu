@@ -519,21 +519,28 @@ int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*fea
 
   EncArgs ea{mw.enc0_t, mw.enc0_b, mw.enc2_t, mw.enc2_b, mw.enc4_t, mw.enc4_b, mw.eln_w, mw.eln_b, mw.centers,
              mw.length_mean, mw.length_std, mw.n_edge_in, mw.use_bond, mw.expand_edge, {box[0], box[1], box[2]}};
+  prof_mark(ctx, "edge_encode", st);
   k_edge_encode<<<grid_edge, NT, smem, st>>>(ea, pos_feat, ctx->col_idx, ctx->edge_dst, ctx->n_edges, orig_id,
                                              ctx->d_bond, atoms_per_frame, ctx->e_emb);
   GAMD_LAUNCH_CHECK();
+  prof_mark(ctx, "edge_encode", st);
 
   NodeArgs na{};
   na.dec0_t = mw.dec0_t; na.dec0_b = mw.dec0_b; na.dec2_w = mw.dec2_w; na.dec2_b = mw.dec2_b;
   na.node_emb = mw.node_emb; na.nenc_w = mw.nenc_w; na.nenc_b = mw.nenc_b;
   na.next = mw.layer[0];
+  prof_mark(ctx, "node_update", st);
   k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, ctx->row_ptr, pos_feat, ctx->agg, ctx->part,
                                                           ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd, ctx->pred);
   GAMD_LAUNCH_CHECK();
+  prof_mark(ctx, "node_update", st);
   for (int l = 0; l < mw.n_layers; l++) {
+    prof_mark(ctx, "mp_edge", st);
     k_mp_edge<<<grid_edge, NT, smem, st>>>(mw.layer[l], ctx->e_emb, ctx->row_ptr, ctx->col_idx, ctx->edge_dst,
                                            ctx->n_edges, ctx->hn, ctx->srcA, ctx->dstA, ctx->agg, ctx->part);
     GAMD_LAUNCH_CHECK();
+    prof_mark(ctx, "mp_edge", st);
+    prof_mark(ctx, "node_update", st);
     na.cur = mw.layer[l];
     if (l + 1 < mw.n_layers) {
       na.next = mw.layer[l + 1];
@@ -546,6 +553,7 @@ int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*fea
                                                               ctx->pd, ctx->pred);
     }
     GAMD_LAUNCH_CHECK();
+    prof_mark(ctx, "node_update", st);
   }
   return 0;
 }

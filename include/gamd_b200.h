@@ -183,6 +183,12 @@ int gamd_check_async_errors(gamd_ctx* ctx, void* stream);
 int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_bytes);
 /* number of kernel launches issued by this ctx since creation */
 int64_t gamd_launch_count(const gamd_ctx* ctx);
+/* per-stage CUDA-event timers on the launching stream.  Stages: "neighbor", "edge_encode",
+ * "mp_edge", "node_update", "integrate".  gamd_profile_read synchronises the device, returns
+ * the device time and the number of timed launches accumulated since the previous read of
+ * that stage, and resets them. */
+int gamd_profile_enable(gamd_ctx* ctx, int32_t on);
+int gamd_profile_read(gamd_ctx* ctx, const char* stage, double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus
 }
