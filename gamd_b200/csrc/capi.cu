@@ -95,14 +95,14 @@ void carve(gamd_ctx* ctx, Carver& c, int64_t A, int64_t E) {
   ctx->err_flag = c.take<int>(4);
   ctx->col_idx = c.take<int>(E);
   ctx->edge_dst = c.take<int>(E);
-  ctx->e_emb = c.take<float>((size_t)E * GAMD_NF);
+  ctx->e_emb = c.take<float>((size_t)(E + 256) * GAMD_NF);   // fp32 rows, or 64 KB bf16 hi/lo blobs per 128-edge tile
   ctx->h = c.take<float>((size_t)A * GAMD_NF);
   ctx->hn = c.take<float>((size_t)A * GAMD_NF);
   ctx->srcA = c.take<float>((size_t)A * GAMD_NF);
   ctx->dstA = c.take<float>((size_t)A * GAMD_NF);
   ctx->pd = c.take<float>((size_t)A * GAMD_NF);
   ctx->agg = c.take<float>((size_t)A * GAMD_NF);
-  ctx->part = c.take<float>((size_t)(E / GAMD_EDGE_TILE + 2) * 2 * GAMD_NF);
+  ctx->part = c.take<float>((size_t)(E / 32 + 4) * 2 * GAMD_NF);
   ctx->pred = c.take<float>((size_t)A * 3);
   ctx->feat_s = c.take<float>(A);
   ctx->stage_a = c.take<double>((size_t)A * 3);
@@ -194,9 +194,9 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
     g_create_err = "node_encoder in_feats must be 1";
     return GAMD_EUNSUPPORTED;
   }
-  if (desc->precision != GAMD_PREC_FP32) {
-    g_create_err = "precision mode not built yet";
-    return GAMD_EUNSUPPORTED;
+  if (desc->precision != GAMD_PREC_FP32 && desc->precision != GAMD_PREC_BF16X3 && desc->precision != GAMD_PREC_BF16) {
+    g_create_err = "unknown precision mode";
+    return GAMD_EINVAL;
   }
   if ((e = cudaSetDevice(device)) != cudaSuccess) {
     g_create_err = cudaGetErrorString(e);
@@ -216,6 +216,8 @@ int gamd_destroy(gamd_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->d_wblob) cudaFree(ctx->d_wblob);
+  if (ctx->d_wimg) cudaFree(ctx->d_wimg);
+  if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
   if (ctx->d_bond) cudaFree(ctx->d_bond);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   delete ctx;
@@ -408,6 +410,54 @@ int gamd_finalize_weights(gamd_ctx* ctx) {
   if (d.use_bond && !ctx->d_bond) {
     ctx->err = "model uses the bond flag: call gamd_set_bonds before gamd_finalize_weights";
     return GAMD_ESTATE;
+  }
+  if (d.precision != GAMD_PREC_FP32) {
+    // tensor-core operand images of the four edge-chain matrices of every layer:
+    // B[n][k] = W[n][k] (torch Linear layout is already N x K, K-major), split x = hi + lo in bf16,
+    // stored in the UMMA canonical SWIZZLE_128B K-major layout (two 64-wide K blocks of 16 KB)
+    auto bf16_rn = [](float x) -> uint16_t {
+      uint32_t u;
+      memcpy(&u, &x, 4);
+      if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+      return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+    };
+    auto bf16_f = [](uint16_t h) -> float {
+      uint32_t u = (uint32_t)h << 16;
+      float f;
+      memcpy(&f, &u, 4);
+      return f;
+    };
+    const size_t chunk = 32768;
+    std::vector<uint8_t> img((size_t)d.conv_layer * 8 * chunk, 0);
+    std::vector<float> tb((size_t)d.conv_layer * 4 * 128, 0.f);
+    const char* names[4] = {"edge_affine.mlp_layer.0", "edge_affine.mlp_layer.2", "theta_edge.mlp_layer.1",
+                            "theta_edge.mlp_layer.3"};
+    for (int l = 0; l < d.conv_layer; l++)
+      for (int s = 0; s < 4; s++) {
+        std::string p = "graph_conv.conv." + std::to_string(l) + "." + names[s];
+        const std::vector<float>& w = ctx->host_w[p + ".weight"];
+        const std::vector<float>& b = ctx->host_w[p + ".bias"];
+        uint8_t* hi = img.data() + ((size_t)(l * 4 + s) * 2 + 0) * chunk;
+        uint8_t* lo = img.data() + ((size_t)(l * 4 + s) * 2 + 1) * chunk;
+        for (int n = 0; n < 128; n++)
+          for (int k = 0; k < 128; k++) {
+            float x = w[(size_t)n * 128 + k];
+            uint16_t h = bf16_rn(x);
+            uint16_t lw = bf16_rn(x - bf16_f(h));
+            size_t off = (size_t)(k >> 6) * 16384 + (size_t)n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + ((k & 7) << 1);
+            memcpy(hi + off, &h, 2);
+            memcpy(lo + off, &lw, 2);
+          }
+        for (int n = 0; n < 128; n++) tb[(size_t)(l * 4 + s) * 128 + n] = b[n];
+      }
+    if (ctx->d_wimg) cudaFree(ctx->d_wimg);
+    if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
+    ctx->d_wimg = nullptr;
+    ctx->d_tc_bias = nullptr;
+    GAMD_CUDA(cudaMalloc(&ctx->d_wimg, img.size()));
+    GAMD_CUDA(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    GAMD_CUDA(cudaMalloc(&ctx->d_tc_bias, tb.size() * sizeof(float)));
+    GAMD_CUDA(cudaMemcpy(ctx->d_tc_bias, tb.data(), tb.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   ctx->finalized = true;
   return 0;

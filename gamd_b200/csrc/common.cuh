@@ -55,6 +55,8 @@ struct gamd_ctx {
   float* d_wblob = nullptr;
   ModelW mw{};
   double scaler_mean = 0.0, scaler_var = 1.0;
+  uint8_t* d_wimg = nullptr;      // tcgen05 weight images: [layer][4 stages][hi,lo][32 KB] SW128 K-major bf16
+  float* d_tc_bias = nullptr;     // [layer][4][128]
   int* d_bond = nullptr;          // [atoms_per_frame][GAMD_MAX_BOND] frame-local partner ids, -1 padded
   int64_t bond_atoms = 0;
 
@@ -132,6 +134,7 @@ int nbr_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float* d_dist, f
 int csr_from_sorted_coo(gamd_ctx* ctx, const int64_t* d_center, const int64_t* d_neigh, int64_t n_atoms, int64_t n_edges, cudaStream_t st);
 int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cudaStream_t st);
 
+int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st);
 int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* feat, const int* orig_id,
                        int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st);
 

@@ -15,6 +15,7 @@
 // in shared memory and the (pre-transposed) weights streamed through a double-buffered
 // cp.async ring.  Arithmetic is fp32 throughout.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -215,7 +216,8 @@ __global__ void __launch_bounds__(NT) k_edge_encode(EncArgs a, const float4* __r
                                                     const int* __restrict__ col, const int* __restrict__ edst,
                                                     const int* __restrict__ n_edges_dev,
                                                     const int* __restrict__ orig_id, const int* __restrict__ bond,
-                                                    int atoms_per_frame, float* __restrict__ e_out) {
+                                                    int atoms_per_frame, float* __restrict__ e_out,
+                                                    uint8_t* __restrict__ e_blob) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -285,7 +287,29 @@ __global__ void __launch_bounds__(NT) k_edge_encode(EncArgs a, const float4* __r
     tile_gemm<NF>(acc, a.enc4_t, sm, tid);
     add_bias(acc, a.enc4_b, tx);
     layer_norm_rows(acc, a.eln_w, a.eln_b, tx);
-    store_rows_global(acc, e_out, e0, E, tx, ty);
+    if (e_blob == nullptr) {
+      store_rows_global(acc, e_out, e0, E, tx, ty);
+    } else {
+      // tensor-core path: bf16 hi / lo split, 64 KB blob per 128-edge tile laid out
+      // [hi | lo][16 k-chunks of 8][128 rows][16 bytes] so that a thread-per-row reader is coalesced
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int e = e0 + ty * 4 + r;
+        if (e >= E) continue;
+        uint8_t* blob = e_blob + (size_t)(e >> 7) * 65536;
+        const int rr = e & 127;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          const int c0 = half * 64 + tx * 4;
+          uint32_t h0, l0, h1, l1;
+          tc::split_bf16(acc[r][half * 4 + 0], acc[r][half * 4 + 1], h0, l0);
+          tc::split_bf16(acc[r][half * 4 + 2], acc[r][half * 4 + 3], h1, l1);
+          const size_t off = ((size_t)(c0 >> 3) * 128 + rr) * 16 + (c0 & 7) * 2;
+          *reinterpret_cast<uint2*>(blob + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(blob + 32768 + off) = make_uint2(l0, l1);
+        }
+      }
+    }
   }
 }
 
@@ -387,7 +411,8 @@ struct NodeArgs {
 };
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(NT) k_node_update(NodeArgs a, int n_atoms, const int* __restrict__ row_ptr,
+__global__ void __launch_bounds__(NT) k_node_update(NodeArgs a, int n_atoms, int agg_tile,
+                                                    const int* __restrict__ row_ptr,
                                                     const float4* __restrict__ pos_feat,
                                                     const float* __restrict__ agg, const float* __restrict__ part,
                                                     float* __restrict__ h, float* __restrict__ hn,
@@ -424,7 +449,7 @@ __global__ void __launch_bounds__(NT) k_node_update(NodeArgs a, int n_atoms, con
         if (i < n_atoms) {
           int rs = row_ptr[i], re = row_ptr[i + 1];
           if (re > rs) {
-            int t0 = rs / GAMD_EDGE_TILE, t1 = (re - 1) / GAMD_EDGE_TILE;
+            int t0 = rs / agg_tile, t1 = (re - 1) / agg_tile;
             if (t0 == t1) {
               v = *reinterpret_cast<const float4*>(agg + (size_t)i * NF + c4 * 4);
             } else {
@@ -520,8 +545,11 @@ int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*fea
   EncArgs ea{mw.enc0_t, mw.enc0_b, mw.enc2_t, mw.enc2_b, mw.enc4_t, mw.enc4_b, mw.eln_w, mw.eln_b, mw.centers,
              mw.length_mean, mw.length_std, mw.n_edge_in, mw.use_bond, mw.expand_edge, {box[0], box[1], box[2]}};
   prof_mark(ctx, "edge_encode", st);
+  const bool tcpath = ctx->desc.precision != GAMD_PREC_FP32;
+  const int agg_tile = tcpath ? 32 : GAMD_EDGE_TILE;
   k_edge_encode<<<grid_edge, NT, smem, st>>>(ea, pos_feat, ctx->col_idx, ctx->edge_dst, ctx->n_edges, orig_id,
-                                             ctx->d_bond, atoms_per_frame, ctx->e_emb);
+                                             ctx->d_bond, atoms_per_frame, ctx->e_emb,
+                                             tcpath ? reinterpret_cast<uint8_t*>(ctx->e_emb) : nullptr);
   GAMD_LAUNCH_CHECK();
   prof_mark(ctx, "edge_encode", st);
 
@@ -530,25 +558,30 @@ int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*fea
   na.node_emb = mw.node_emb; na.nenc_w = mw.nenc_w; na.nenc_b = mw.nenc_b;
   na.next = mw.layer[0];
   prof_mark(ctx, "node_update", st);
-  k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, ctx->row_ptr, pos_feat, ctx->agg, ctx->part,
+  k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg, ctx->part,
                                                           ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd, ctx->pred);
   GAMD_LAUNCH_CHECK();
   prof_mark(ctx, "node_update", st);
   for (int l = 0; l < mw.n_layers; l++) {
     prof_mark(ctx, "mp_edge", st);
-    k_mp_edge<<<grid_edge, NT, smem, st>>>(mw.layer[l], ctx->e_emb, ctx->row_ptr, ctx->col_idx, ctx->edge_dst,
-                                           ctx->n_edges, ctx->hn, ctx->srcA, ctx->dstA, ctx->agg, ctx->part);
-    GAMD_LAUNCH_CHECK();
+    if (tcpath) {
+      int rc = mp_edge_tc_launch(ctx, l, st);
+      if (rc) return rc;
+    } else {
+      k_mp_edge<<<grid_edge, NT, smem, st>>>(mw.layer[l], ctx->e_emb, ctx->row_ptr, ctx->col_idx, ctx->edge_dst,
+                                             ctx->n_edges, ctx->hn, ctx->srcA, ctx->dstA, ctx->agg, ctx->part);
+      GAMD_LAUNCH_CHECK();
+    }
     prof_mark(ctx, "mp_edge", st);
     prof_mark(ctx, "node_update", st);
     na.cur = mw.layer[l];
     if (l + 1 < mw.n_layers) {
       na.next = mw.layer[l + 1];
-      k_node_update<false, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, ctx->row_ptr, pos_feat, ctx->agg,
+      k_node_update<false, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
                                                                ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA,
                                                                ctx->pd, ctx->pred);
     } else {
-      k_node_update<false, true><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, ctx->row_ptr, pos_feat, ctx->agg,
+      k_node_update<false, true><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
                                                               ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA,
                                                               ctx->pd, ctx->pred);
     }
