@@ -11,9 +11,9 @@
 //   precision "bf16x3": x = hi + lo (two bf16), D = Ahi*Bhi + Alo*Bhi + Ahi*Blo  -> fp32-grade result
 //   precision "bf16"  : single pass on the hi parts
 //
-// CTA = 10 warps: 2 epilogue warpgroups (thread = edge row; each owns one 128-edge tile in flight, the two
-// tiles ping-pong on the tensor core and share every weight load), 1 MMA-issue warp, 1 weight-producer
-// warp.  Neighbour features are gathered with coalesced cp.async into per-warp staging rows; the final
+// CTA = 18 warps: 16 epilogue warps (thread = edge row; two 128-edge tiles in flight, 8 warps each = 4 TMEM
+// lane quadrants x 2 column halves; the two tiles ping-pong on the tensor core and share every weight
+// load), 1 MMA-issue warp, 1 weight-producer warp.  Neighbour features are gathered with coalesced cp.async into per-warp staging rows; the final
 // segmented sum is a warp-shuffle segmented scan over the receiver-sorted rows - no atomics; rows
 // that straddle a 32-edge block go to the `part` side buffer and are summed (in order) by the node kernel.
 #include "common.cuh"
@@ -25,9 +25,10 @@ using namespace tc;
 constexpr int TILE = 128;
 constexpr int WCHUNK = 32768;        // one weight part image (128 x 128 bf16)
 constexpr int RING = 4;
-constexpr int GROW = 144;            // staging row stride in bytes (128 data + 16 pad: conflict-free LDS.128)
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 320;
+constexpr int GROW = 80;             // staging row stride in bytes (64 data + 16 pad: conflict-free LDS.128)
+constexpr int EPI_WARPS = 16;        // 2 tiles in flight x 4 lane quadrants x 2 column halves
+constexpr int MMA_WARP = EPI_WARPS;   // warp EPI_WARPS + 1 is the weight producer
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
 
 struct __align__(1024) SmemTC {
   uint8_t w[RING][WCHUNK];
@@ -63,6 +64,151 @@ __device__ __forceinline__ float silu_fast(float x) {
   return x * r;
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
+
+// per-thread state of an epilogue thread for the tile it is working on
+struct EpiCtx {
+  uint32_t Dc, AH, AL;          // TMEM addresses (my lane quadrant, my 64-column half of my tile slot)
+  uint32_t gbuf[2];             // shared addresses of my warp's two gather staging buffers
+  uint32_t grow_off;            // my row inside a staging buffer (lane * GROW)
+  uint32_t gl_dst;              // cp.async destination offset of this lane: (lane>>2)*GROW + (lane&3)*16
+  int gl_row, gl_col;           // cp.async source row (lane>>2) and float offset ((lane&3)*4)
+  uint32_t bias_addr;           // shared address of bias[0][col0]
+  int col0, src;
+  bool valid;
+  uint32_t same;
+  float* out_row;
+  const float4* dst_row;
+  const float *srcA, *hn;
+};
+
+// gather #gi of the current tile: gi = 0..7 -> (array = gi<4 ? srcA : hn, 16-column chunk = gi&3);
+// 64 B of each of my warp's 32 neighbour rows, coalesced: 4 lanes per row, 8 rows per instruction
+__device__ __forceinline__ void issue_gather(const EpiCtx& c, int gi) {
+  const float* base = (gi < 4 ? c.srcA : c.hn) + c.col0 + (gi & 3) * 16 + c.gl_col;
+  const uint32_t dst = c.gbuf[gi & 1] + c.gl_dst;
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const int sj = __shfl_sync(0xffffffffu, c.src, it * 8 + c.gl_row);
+    cp_async16s(dst + it * 8 * GROW, base + (size_t)sj * 128);
+  }
+  cp_async_commit();
+}
+
+__device__ __forceinline__ float silu_tanh(float x) {
+  // x * sigmoid(x) = 0.5 x (1 + tanh(x/2)) with one MUFU.TANH (rel. error 2^-11: bf16 "fast" mode only)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+// epilogue of GEMM stage S for my 64 columns (4 chunks of 16)
+template <int S, bool EXACT>
+__device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
+  float4 dn[4];
+  if (S == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) dn[i] = __ldg(c.dst_row + i);
+  }
+  uint32_t vbuf[2][16];
+  tmem_ld16(c.Dc, vbuf[0]);
+#pragma unroll
+  for (int cc = 0; cc < 4; cc++) {
+    // TMEM loads are pipelined one chunk ahead: wait for chunk cc, then put chunk cc+1 in flight
+    tmem_wait_ld();
+    if (cc < 3) tmem_ld16(c.Dc + (cc + 1) * 16, vbuf[(cc + 1) & 1]);
+    const uint32_t(&v)[16] = vbuf[cc & 1];
+    uint32_t grow = 0;
+    float4 dc[4];
+    if (S == 1 || S == 3) {
+      // software pipeline over the 8 gathers of this tile: srcA chunks 0-3 (stage 1), hn chunks 0-3 (stage 3)
+      const int gi = (S == 1 ? 0 : 4) + cc;
+      if (gi + 1 < 8) {
+        issue_gather(c, gi + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      grow = c.gbuf[gi & 1] + c.grow_off;
+      if (S == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) dc[i] = dn[i];
+        if (cc < 3) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) dn[i] = __ldg(c.dst_row + (cc + 1) * 4 + i);
+        }
+      }
+    }
+    float x[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; j4++) {
+      const float4 b = lds128(c.bias_addr + (S * 128 + cc * 16 + j4 * 4) * 4);
+      x[4 * j4] = __uint_as_float(v[4 * j4]) + b.x;
+      x[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+      x[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
+      x[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+    }
+    if (S == 1) {
+#pragma unroll
+      for (int j4 = 0; j4 < 4; j4++) {
+        const float4 sv = lds128(grow + j4 * 16);
+        x[4 * j4] += sv.x + dc[j4].x;
+        x[4 * j4 + 1] += sv.y + dc[j4].y;
+        x[4 * j4 + 2] += sv.z + dc[j4].z;
+        x[4 * j4 + 3] += sv.w + dc[j4].w;
+      }
+    }
+    if (S < 3) {
+      uint32_t h[8], l[8];
+      if (EXACT) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) split_bf16(silu_fast(x[2 * j]), silu_fast(x[2 * j + 1]), h[j], l[j]);
+        tmem_st8(c.AH + cc * 8, h);
+        tmem_st8(c.AL + cc * 8, l);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) h[j] = pack_bf16(silu_tanh(x[2 * j]), silu_tanh(x[2 * j + 1]));
+        tmem_st8(c.AH + cc * 8, h);
+      }
+    } else {
+      // message = hn[src] * e_emb, then segmented inclusive scan down the receiver-sorted rows
+#pragma unroll
+      for (int j4 = 0; j4 < 4; j4++) {
+        const float4 hv = lds128(grow + j4 * 16);
+        x[4 * j4] = c.valid ? x[4 * j4] * hv.x : 0.f;
+        x[4 * j4 + 1] = c.valid ? x[4 * j4 + 1] * hv.y : 0.f;
+        x[4 * j4 + 2] = c.valid ? x[4 * j4 + 2] * hv.z : 0.f;
+        x[4 * j4 + 3] = c.valid ? x[4 * j4 + 3] * hv.w : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const bool take = (c.same >> k) & 1u;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const float u = __shfl_up_sync(0xffffffffu, x[j], 1 << k);
+          if (take) x[j] += u;
+        }
+      }
+      if (c.out_row) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++)
+          *reinterpret_cast<float4*>(c.out_row + cc * 16 + j4 * 4) =
+              make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
   SmemTC& sm = *reinterpret_cast<SmemTC*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -71,14 +217,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
   const int ntiles = (E + TILE - 1) / TILE;
   const int npairs = (ntiles + 1) / 2;
 
-  if (warp == 8) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base, 512);
   if (tid == 0) {
     for (int i = 0; i < RING; i++) {
       mbar_init(&sm.full[i], 1);
       mbar_init(&sm.empty[i], 1);
     }
     for (int g = 0; g < 2; g++) {
-      mbar_init(&sm.a_ready[g], 128);
+      mbar_init(&sm.a_ready[g], 256);
       mbar_init(&sm.d_ready[g], 1);
     }
     fence_barrier_init();
@@ -90,170 +236,113 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
   const uint32_t tb = sm.tmem_base;
 
   if (warp < EPI_WARPS) {
-    // ===================== epilogue warpgroups: thread = edge row =====================
-    const int g = warp >> 2, wq = warp & 3;
+    // ===== epilogue warps: thread = edge row; warp = (tile slot g, column half ch, lane quadrant wq) =====
+    const int g = warp >> 3, ch = (warp >> 2) & 1, wq = warp & 3;
     const int r = wq * 32 + lane;
+    const bool exact = a.exact != 0;
+    EpiCtx c;
+    c.col0 = ch * 64;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    const uint32_t Dc = tb + lane_base + g * 256, AH = Dc + 128, AL = Dc + 192;
-    uint8_t* gbuf0 = sm.gather[warp][0];
-    uint8_t* gbuf1 = sm.gather[warp][1];
+    c.Dc = tb + lane_base + g * 256 + c.col0;
+    c.AH = tb + lane_base + g * 256 + 128 + c.col0 / 2;
+    c.AL = c.AH + 64;
+    c.gbuf[0] = smem_u32(sm.gather[warp][0]);
+    c.gbuf[1] = smem_u32(sm.gather[warp][1]);
+    c.grow_off = lane * GROW;
+    c.gl_row = lane >> 2;
+    c.gl_col = (lane & 3) * 4;
+    c.gl_dst = (lane >> 2) * GROW + (lane & 3) * 16;
+    c.bias_addr = smem_u32(&sm.bias[0][c.col0]);
+    c.srcA = a.srcA;
+    c.hn = a.hn;
+    uint64_t* const a_bar = &sm.a_ready[g];
+    uint64_t* const d_bar = &sm.d_ready[g];
     uint32_t d_par = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int tile = pair * 2 + g;
       if (tile >= ntiles) continue;
       const int e0 = tile * TILE;
       const int e = e0 + r;
-      const bool valid = e < E;
-      const int src = valid ? a.col[e] : 0;
-      const int dst = valid ? a.edst[e] : -1;
-      const int dstc = dst < 0 ? 0 : dst;
-
-      auto issue_gather = [&](const float* base, int c, uint8_t* buf) {
-        __syncwarp();
+      c.valid = e < E;
+      c.src = c.valid ? a.col[e] : 0;
+      const int dst = c.valid ? a.edst[e] : -1;
+      c.dst_row = reinterpret_cast<const float4*>(a.dstA + (size_t)(dst < 0 ? 0 : dst) * 128 + c.col0);
+      issue_gather(c, 0);
+      {  // pull my share of the NEXT tile's e blob into L2 while this tile is being processed
+        const int ntile = tile + 2 * (int)gridDim.x;
+        if (ntile < ntiles && (lane & 7) == 0) {
+          const uint8_t* nb = a.e_blob + (size_t)ntile * 65536 + ((size_t)(ch * 8) * 128 + r) * 16;
 #pragma unroll
-        for (int it = 0; it < 8; it++) {
-          int j = it * 4 + (lane >> 3);
-          int sj = __shfl_sync(0xffffffffu, src, j);
-          cp_async16(buf + j * GROW + (lane & 7) * 16, base + (size_t)sj * 128 + c * 32 + (lane & 7) * 4);
-        }
-        cp_async_commit();
-      };
-      issue_gather(a.srcA, 0, gbuf0);   // gather #0 (stage-1 chunk 0)
-
-      // ---- stage 0 operand: e tile (bf16 hi / lo) -> TMEM A -----------------------------
-      {
-        const uint4* bh = reinterpret_cast<const uint4*>(a.e_blob + (size_t)tile * 65536);
-        const uint4* bl = reinterpret_cast<const uint4*>(a.e_blob + (size_t)tile * 65536 + 32768);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-          uint32_t h[16];
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            uint4 q = __ldg(bh + (c4 * 4 + i) * 128 + r);
-            h[4 * i] = q.x; h[4 * i + 1] = q.y; h[4 * i + 2] = q.z; h[4 * i + 3] = q.w;
+          for (int i = 0; i < 8; i++) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + i * 2048));
+            if (exact) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + 32768 + i * 2048));
           }
-          tmem_st16(AH + c4 * 16, h);
-          if (a.exact) {
+        }
+      }
+
+      // ---- stage 0 operand: my half of the e tile (bf16 hi / lo) -> TMEM A ------------------
+      {
+        const uint4* bh = reinterpret_cast<const uint4*>(a.e_blob + (size_t)tile * 65536) + (ch * 8) * 128 + r;
+#pragma unroll
+        for (int part = 0; part < 2; part++) {
+          if (part == 1 && !exact) break;
+          const uint4* bp = bh + part * (32768 / 16);
+          uint4 q[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) q[i] = __ldg(bp + i * 128);
+#pragma unroll
+          for (int c2 = 0; c2 < 2; c2++) {
+            uint32_t h[16];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-              uint4 q = __ldg(bl + (c4 * 4 + i) * 128 + r);
-              h[4 * i] = q.x; h[4 * i + 1] = q.y; h[4 * i + 2] = q.z; h[4 * i + 3] = q.w;
+              h[4 * i] = q[c2 * 4 + i].x; h[4 * i + 1] = q[c2 * 4 + i].y;
+              h[4 * i + 2] = q[c2 * 4 + i].z; h[4 * i + 3] = q[c2 * 4 + i].w;
             }
-            tmem_st16(AL + c4 * 16, h);
+            tmem_st16((part ? c.AL : c.AH) + c2 * 16, h);
           }
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&sm.a_ready[g]);
+        mbar_arrive(a_bar);
       }
 
       // segment structure of my warp's 32 rows (receiver-sorted)
-      uint32_t same = 0;   // bit k: row (lane - 2^k) belongs to my segment
+      c.same = 0;   // bit k: row (lane - 2^k) belongs to my segment
 #pragma unroll
       for (int k = 0; k < 5; k++) {
-        int od = __shfl_up_sync(0xffffffffu, dst, 1 << k);
-        if (lane >= (1 << k) && od == dst) same |= 1u << k;
+        const int od = __shfl_up_sync(0xffffffffu, dst, 1 << k);
+        if (lane >= (1 << k) && od == dst) c.same |= 1u << k;
       }
       const int nd = __shfl_down_sync(0xffffffffu, dst, 1);
-      const bool seg_end = valid && (lane == 31 || nd != dst);
-      float* out_row = nullptr;
-      if (seg_end) {
+      c.out_row = nullptr;
+      if (c.valid && (lane == 31 || nd != dst)) {
         const int bstart = e0 + wq * 32;
         const int bend = min(bstart + 32, E);
         const int blk = bstart >> 5;
-        if (a.row_ptr[dst] < bstart) out_row = a.part + ((size_t)blk * 2 + 0) * 128;
-        else if (a.row_ptr[dst + 1] > bend) out_row = a.part + ((size_t)blk * 2 + 1) * 128;
-        else out_row = a.agg + (size_t)dst * 128;
+        if (a.row_ptr[dst] < bstart) c.out_row = a.part + ((size_t)blk * 2 + 0) * 128;
+        else if (a.row_ptr[dst + 1] > bend) c.out_row = a.part + ((size_t)blk * 2 + 1) * 128;
+        else c.out_row = a.agg + (size_t)dst * 128;
+        c.out_row += c.col0;
       }
 
-#pragma unroll 1
-      for (int s = 0; s < 4; s++) {
-        mbar_wait(&sm.d_ready[g], d_par);
-        d_par ^= 1;
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 4; c++) {
-          uint32_t v0[16], v1[16];
-          tmem_ld16(Dc + c * 32, v0);
-          tmem_ld16(Dc + c * 32 + 16, v1);
-          const uint8_t* grow = nullptr;
-          if (s == 1 || s == 3) {
-            // software pipeline over the 8 gathers of this tile: srcA chunks 0-3, then hn chunks 0-3
-            const int gi = (s == 1 ? 0 : 4) + c;
-            uint8_t* cur = (gi & 1) ? gbuf1 : gbuf0;
-            uint8_t* nxt = (gi & 1) ? gbuf0 : gbuf1;
-            if (gi + 1 < 8) {
-              issue_gather(gi + 1 < 4 ? a.srcA : a.hn, (gi + 1) & 3, nxt);
-              cp_async_wait<1>();
-            } else {
-              cp_async_wait<0>();
-            }
-            __syncwarp();
-            grow = cur + lane * GROW;
-          }
-          tmem_wait_ld();
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            x[j] = __uint_as_float(v0[j]);
-            x[16 + j] = __uint_as_float(v1[j]);
-          }
-#pragma unroll
-          for (int j4 = 0; j4 < 8; j4++) {
-            float4 b = *reinterpret_cast<const float4*>(&sm.bias[s][c * 32 + j4 * 4]);
-            x[4 * j4] += b.x; x[4 * j4 + 1] += b.y; x[4 * j4 + 2] += b.z; x[4 * j4 + 3] += b.w;
-          }
-          if (s == 1) {
-            const float4* dr = reinterpret_cast<const float4*>(a.dstA + (size_t)dstc * 128 + c * 32);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; j4++) {
-              float4 sv = *reinterpret_cast<const float4*>(grow + j4 * 16);
-              float4 dv = __ldg(dr + j4);
-              x[4 * j4] += sv.x + dv.x; x[4 * j4 + 1] += sv.y + dv.y;
-              x[4 * j4 + 2] += sv.z + dv.z; x[4 * j4 + 3] += sv.w + dv.w;
-            }
-          }
-          if (s < 3) {
-            uint32_t h[16], l[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) split_bf16(silu_fast(x[2 * j]), silu_fast(x[2 * j + 1]), h[j], l[j]);
-            tmem_st16(AH + c * 16, h);
-            if (a.exact) tmem_st16(AL + c * 16, l);
-          } else {
-            // message = hn[src] * e_emb, then segmented inclusive scan down the receiver-sorted rows
-#pragma unroll
-            for (int j4 = 0; j4 < 8; j4++) {
-              float4 hv = *reinterpret_cast<const float4*>(grow + j4 * 16);
-              x[4 * j4] = valid ? x[4 * j4] * hv.x : 0.f;
-              x[4 * j4 + 1] = valid ? x[4 * j4 + 1] * hv.y : 0.f;
-              x[4 * j4 + 2] = valid ? x[4 * j4 + 2] * hv.z : 0.f;
-              x[4 * j4 + 3] = valid ? x[4 * j4 + 3] * hv.w : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-              const bool take = (same >> k) & 1u;
-#pragma unroll
-              for (int j = 0; j < 32; j++) {
-                float t = __shfl_up_sync(0xffffffffu, x[j], 1 << k);
-                if (take) x[j] += t;
-              }
-            }
-            if (out_row) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; j4++)
-                *reinterpret_cast<float4*>(out_row + c * 32 + j4 * 4) =
-                    make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
-            }
-          }
-        }
-        if (s < 3) {
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(&sm.a_ready[g]);
-        }
-      }
+#define GAMD_STAGE(S)                              \
+  mbar_wait(d_bar, d_par);                         \
+  d_par ^= 1;                                      \
+  tc_fence_after();                                \
+  if (exact) stage_epilogue<S, true>(c);           \
+  else stage_epilogue<S, false>(c);                \
+  if (S < 3) {                                     \
+    tmem_wait_st();                                \
+    tc_fence_before();                             \
+    mbar_arrive(a_bar);                            \
+  }
+      GAMD_STAGE(0)
+      GAMD_STAGE(1)
+      GAMD_STAGE(2)
+      GAMD_STAGE(3)
+#undef GAMD_STAGE
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ===================== MMA issue (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 128);
@@ -330,7 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tb, 512);
+  if (warp == MMA_WARP) tmem_dealloc(tb, 512);
 }
 
 }  // namespace

@@ -81,6 +81,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // ---- UMMA descriptors ----------------------------------------------------------------------------
 // K-major operand tile, SWIZZLE_128B: rows of 128 bytes (64 bf16 of K), 16-byte chunk c of row r stored
 // at chunk (c ^ (r & 7)); 8-row groups 1024 bytes apart (SBO); tile base 1024-byte aligned.
@@ -126,10 +132,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {   
   return *reinterpret_cast<uint32_t*>(&v);
 }
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): packs two elements into (hi pair, lo pair)
+// (one packed F2FP conversion per pair for each part; the hi values are recovered with bit operations,
+// so no scalar F2F conversions - those run on the 16-lane XU pipe - are needed)
 __device__ __forceinline__ void split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
-  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  hi = pack_bf16(a, b);
+  float ar = a - __uint_as_float(hi << 16), br = b - __uint_as_float(hi & 0xffff0000u);
   lo = pack_bf16(ar, br);
 }
 
