@@ -218,6 +218,8 @@ int gamd_destroy(gamd_ctx* ctx) {
   if (ctx->d_wblob) cudaFree(ctx->d_wblob);
   if (ctx->d_wimg) cudaFree(ctx->d_wimg);
   if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
+  if (ctx->d_wimg_enc) cudaFree(ctx->d_wimg_enc);
+  if (ctx->d_tc_bias_enc) cudaFree(ctx->d_tc_bias_enc);
   if (ctx->d_bond) cudaFree(ctx->d_bond);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   delete ctx;
@@ -458,6 +460,38 @@ int gamd_finalize_weights(gamd_ctx* ctx) {
     GAMD_CUDA(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
     GAMD_CUDA(cudaMalloc(&ctx->d_tc_bias, tb.size() * sizeof(float)));
     GAMD_CUDA(cudaMemcpy(ctx->d_tc_bias, tb.data(), tb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // edge encoder: enc0 [128 x n_in] zero-padded to K = 64 (one K block), enc2 / enc4 [128 x 128]
+    {
+      std::vector<uint8_t> eimg(2 * 16384 + 4 * 32768, 0);
+      std::vector<float> eb(3 * 128, 0.f);
+      const char* en[3] = {"edge_encoder.mlp_layer.0", "edge_encoder.mlp_layer.2", "edge_encoder.mlp_layer.4"};
+      size_t base = 0;
+      for (int s = 0; s < 3; s++) {
+        const std::vector<float>& w = ctx->host_w[std::string(en[s]) + ".weight"];
+        const std::vector<float>& b = ctx->host_w[std::string(en[s]) + ".bias"];
+        const int K = s == 0 ? n_in : 128;
+        const size_t part = s == 0 ? 16384 : 32768;
+        for (int n = 0; n < 128; n++)
+          for (int k = 0; k < K; k++) {
+            float x = w[(size_t)n * K + k];
+            uint16_t h = bf16_rn(x);
+            uint16_t lw = bf16_rn(x - bf16_f(h));
+            size_t off = (size_t)(k >> 6) * 16384 + (size_t)n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + ((k & 7) << 1);
+            memcpy(eimg.data() + base + off, &h, 2);
+            memcpy(eimg.data() + base + part + off, &lw, 2);
+          }
+        for (int n = 0; n < 128; n++) eb[(size_t)s * 128 + n] = b[n];
+        base += 2 * part;
+      }
+      if (ctx->d_wimg_enc) cudaFree(ctx->d_wimg_enc);
+      if (ctx->d_tc_bias_enc) cudaFree(ctx->d_tc_bias_enc);
+      ctx->d_wimg_enc = nullptr;
+      ctx->d_tc_bias_enc = nullptr;
+      GAMD_CUDA(cudaMalloc(&ctx->d_wimg_enc, eimg.size()));
+      GAMD_CUDA(cudaMemcpy(ctx->d_wimg_enc, eimg.data(), eimg.size(), cudaMemcpyHostToDevice));
+      GAMD_CUDA(cudaMalloc(&ctx->d_tc_bias_enc, eb.size() * sizeof(float)));
+      GAMD_CUDA(cudaMemcpy(ctx->d_tc_bias_enc, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
   }
   ctx->finalized = true;
   return 0;

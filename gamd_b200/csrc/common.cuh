@@ -57,6 +57,8 @@ struct gamd_ctx {
   double scaler_mean = 0.0, scaler_var = 1.0;
   uint8_t* d_wimg = nullptr;      // tcgen05 weight images: [layer][4 stages][hi,lo][32 KB] SW128 K-major bf16
   float* d_tc_bias = nullptr;     // [layer][4][128]
+  uint8_t* d_wimg_enc = nullptr;  // edge encoder images: enc0 hi|lo (16 KB each, K=64), enc2 hi|lo, enc4 hi|lo (32 KB each)
+  float* d_tc_bias_enc = nullptr; // [3][128]
   int* d_bond = nullptr;          // [atoms_per_frame][GAMD_MAX_BOND] frame-local partner ids, -1 padded
   int64_t bond_atoms = 0;
 
@@ -135,6 +137,8 @@ int csr_from_sorted_coo(gamd_ctx* ctx, const int64_t* d_center, const int64_t* d
 int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cudaStream_t st);
 
 int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st);
+int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int atoms_per_frame,
+                          const float box[3], cudaStream_t st);
 int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* feat, const int* orig_id,
                        int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st);
 

@@ -547,10 +547,14 @@ int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*fea
   prof_mark(ctx, "edge_encode", st);
   const bool tcpath = ctx->desc.precision != GAMD_PREC_FP32;
   const int agg_tile = tcpath ? 32 : GAMD_EDGE_TILE;
-  k_edge_encode<<<grid_edge, NT, smem, st>>>(ea, pos_feat, ctx->col_idx, ctx->edge_dst, ctx->n_edges, orig_id,
-                                             ctx->d_bond, atoms_per_frame, ctx->e_emb,
-                                             tcpath ? reinterpret_cast<uint8_t*>(ctx->e_emb) : nullptr);
-  GAMD_LAUNCH_CHECK();
+  if (tcpath) {
+    int rc = edge_encode_tc_launch(ctx, pos_feat, orig_id, atoms_per_frame, box, st);
+    if (rc) return rc;
+  } else {
+    k_edge_encode<<<grid_edge, NT, smem, st>>>(ea, pos_feat, ctx->col_idx, ctx->edge_dst, ctx->n_edges, orig_id,
+                                               ctx->d_bond, atoms_per_frame, ctx->e_emb, nullptr);
+    GAMD_LAUNCH_CHECK();
+  }
   prof_mark(ctx, "edge_encode", st);
 
   NodeArgs na{};
