@@ -59,6 +59,11 @@ SIGNATURES = {
                               c_float, c_void_p, c_double, c_int32, c_void_p, c_void_p]),
     "gamd_md_step_host": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                     POINTER(c_double), c_float, c_void_p, c_double]),
+    "gamd_dd_begin": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_double), c_float, c_void_p, c_void_p]),
+    "gamd_dd_layer": (c_int32, [c_void_p, c_int32, c_void_p]),
+    "gamd_dd_pack_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "gamd_dd_unpack_rows": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "gamd_dd_finish": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p]),
     "gamd_check_async_errors": (c_int32, [c_void_p, c_void_p]),
     "gamd_debug_ptr": (c_int32, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
     "gamd_launch_count": (c_int64, [c_void_p]),
@@ -225,6 +230,23 @@ class Context:
     def md_step_host(self, x, v, f, mass, box, cutoff, dt, feat=None, n_frames=1):
         self._check(self.lib.gamd_md_step_host(self._h, _ptr(x), _ptr(v), _ptr(f), _ptr(mass), x.shape[0], n_frames,
                                                _box3(box), float(cutoff), _ptr(feat), float(dt)))
+
+    # ---- domain decomposition ----
+    def dd_begin(self, pos_f64, n_own, box, cutoff, feat=None):
+        self._check(self.lib.gamd_dd_begin(self._h, _ptr(pos_f64), int(n_own), pos_f64.shape[0], _box3(box),
+                                           float(cutoff), _ptr(feat), _stream()))
+
+    def dd_layer(self, layer):
+        self._check(self.lib.gamd_dd_layer(self._h, int(layer), _stream()))
+
+    def dd_pack_rows(self, local_idx_i32, out):
+        self._check(self.lib.gamd_dd_pack_rows(self._h, _ptr(local_idx_i32), local_idx_i32.shape[0], _ptr(out), _stream()))
+
+    def dd_unpack_rows(self, first_local_idx, buf, n):
+        self._check(self.lib.gamd_dd_unpack_rows(self._h, int(first_local_idx), int(n), _ptr(buf), _stream()))
+
+    def dd_finish(self, force, v=None, mass=None, dt=0.0, ke=None):
+        self._check(self.lib.gamd_dd_finish(self._h, _ptr(force), _ptr(v), _ptr(mass), float(dt), _ptr(ke), _stream()))
 
     def check_async_errors(self):
         self._check(self.lib.gamd_check_async_errors(self._h, _stream()))

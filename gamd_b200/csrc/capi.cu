@@ -86,6 +86,7 @@ void carve(gamd_ctx* ctx, Carver& c, int64_t A, int64_t E) {
   ctx->pos_nbr_s = c.take<float4>(A);
   ctx->pos_feat_s = c.take<float4>(A);
   ctx->perm = c.take<int>(A);
+  ctx->inv_perm = c.take<int>(A);
   ctx->cell_start = c.take<int>(ctx->cap_cells + 1);
   ctx->deg = c.take<int>(A + 1);
   ctx->row_ptr = c.take<int>(A + 1);
@@ -155,6 +156,29 @@ void prof_mark(gamd_ctx* ctx, const char* stage, cudaStream_t st) {
     p.ev.push_back(e);
   }
   cudaEventRecord(p.ev[p.used++], st);
+}
+
+__global__ void k_dd_pack(const int* __restrict__ idx, const int* __restrict__ inv_perm, int64_t n,
+                          const float* __restrict__ hn, const float* __restrict__ srcA, float* __restrict__ out) {
+  // one warp per row: out[k] = [hn row | srcA row] of local atom idx[k]
+  int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (k >= n) return;
+  int s = inv_perm[idx[k]];
+  float4 a = reinterpret_cast<const float4*>(hn + (size_t)s * 128)[lane];
+  float4 b = reinterpret_cast<const float4*>(srcA + (size_t)s * 128)[lane];
+  reinterpret_cast<float4*>(out + (size_t)k * 256)[lane] = a;
+  reinterpret_cast<float4*>(out + (size_t)k * 256 + 128)[lane] = b;
+}
+
+__global__ void k_dd_unpack(int64_t first, const int* __restrict__ inv_perm, int64_t n, const float* __restrict__ in,
+                            float* __restrict__ hn, float* __restrict__ srcA) {
+  int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (k >= n) return;
+  int s = inv_perm[first + k];
+  reinterpret_cast<float4*>(hn + (size_t)s * 128)[lane] = reinterpret_cast<const float4*>(in + (size_t)k * 256)[lane];
+  reinterpret_cast<float4*>(srcA + (size_t)s * 128)[lane] = reinterpret_cast<const float4*>(in + (size_t)k * 256 + 128)[lane];
 }
 
 int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st) {
@@ -663,6 +687,63 @@ int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, cons
   GAMD_CUDA(cudaMemcpyAsync(h_v, ctx->stage_b, b3, cudaMemcpyDeviceToHost, st));
   GAMD_CUDA(cudaMemcpyAsync(h_f, ctx->stage_c, b3, cudaMemcpyDeviceToHost, st));
   return gamd_check_async_errors(ctx, st);
+}
+
+int gamd_dd_begin(gamd_ctx* ctx, const double* d_pos, int64_t n_own, int64_t n_local, const double h_box[3],
+                  float cutoff, const float* d_feat, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!d_pos || !h_box || n_own <= 0 || n_local < n_own) return GAMD_EINVAL;
+  if (ctx->desc.kind != GAMD_MODEL_LJ && !d_feat) {
+    ctx->err = "this model needs the node feature vector";
+    return GAMD_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float boxf[3] = {(float)h_box[0], (float)h_box[1], (float)h_box[2]};
+  NbrParams p;
+  if ((rc = nbr_setup_params(ctx, n_local, 1, boxf, cutoff, GAMD_NBR_LT | GAMD_NBR_SELF, &p))) return rc;
+  p.n_centers = (int)n_own;
+  prof_mark(ctx, "neighbor", st);
+  if ((rc = nbr_bin_f64(ctx, d_pos, 1.0, h_box, p, st))) return rc;
+  if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
+  prof_mark(ctx, "neighbor", st);
+  ctx->dd_n_own = n_own;
+  ctx->dd_n_loc = n_local;
+  return model_begin(ctx, ctx->pos_feat_s, ctx->perm, n_local, (int)n_local, boxf, st);
+}
+
+int gamd_dd_layer(gamd_ctx* ctx, int32_t layer, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (ctx->dd_n_loc <= 0 || layer < 0 || layer >= ctx->mw.n_layers) return GAMD_EINVAL;
+  return model_layer(ctx, layer, ctx->pos_feat_s, ctx->dd_n_loc, (cudaStream_t)stream);
+}
+
+int gamd_dd_pack_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, float* d_out, void* stream) {
+  if (!ctx || ctx->dd_n_loc <= 0 || n < 0 || (n > 0 && (!d_local_idx || !d_out))) return GAMD_EINVAL;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_dd_pack<<<ceil_div(n * 32, 256), 256, 0, st>>>(d_local_idx, ctx->inv_perm, n, ctx->hn, ctx->srcA, d_out);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int gamd_dd_unpack_rows(gamd_ctx* ctx, int64_t first_local_idx, int64_t n, const float* d_in, void* stream) {
+  if (!ctx || ctx->dd_n_loc <= 0 || n < 0 || first_local_idx < 0 || first_local_idx + n > ctx->dd_n_loc ||
+      (n > 0 && !d_in))
+    return GAMD_EINVAL;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_dd_unpack<<<ceil_div(n * 32, 256), 256, 0, st>>>(first_local_idx, ctx->inv_perm, n, d_in, ctx->hn, ctx->srcA);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int gamd_dd_finish(gamd_ctx* ctx, double* d_force, double* d_v, const double* d_mass, double dt, double* d_ke,
+                   void* stream) {
+  if (!ctx || ctx->dd_n_loc <= 0 || !d_force || (d_v && !d_mass)) return GAMD_EINVAL;
+  return integ_denorm_scatter(ctx, ctx->perm, d_force, d_v, d_mass, dt, ctx->dd_n_loc, d_ke, (cudaStream_t)stream,
+                              ctx->dd_n_own);
 }
 
 int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_bytes) {

@@ -18,6 +18,7 @@ struct NbrParams {
   int nc[3];
   int cells_per_frame;
   int n_atoms, atoms_per_frame, n_frames;
+  int n_centers;   // atoms with caller index >= n_centers are neighbours only (halo atoms): no CSR row
   float rc, rc2;
   int flags;
 };
@@ -81,6 +82,7 @@ struct gamd_ctx {
   // model
   float *e_emb = nullptr, *h = nullptr, *hn = nullptr, *srcA = nullptr, *dstA = nullptr, *pd = nullptr;
   float *agg = nullptr, *part = nullptr, *pred = nullptr;
+  int* inv_perm = nullptr;                                    // caller index -> sorted index (domain decomposition)
   float* feat_s = nullptr;                                    // node type feature in sorted order
   // export helpers
   int *deg_o = nullptr, *row_ptr_o = nullptr;
@@ -91,6 +93,7 @@ struct gamd_ctx {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   NbrParams last_nbr{};
+  int64_t dd_n_own = 0, dd_n_loc = 0;   // domain decomposition: owned / owned + halo atoms of the step in flight
   int sm_count = 148;
 
   // optional per-stage CUDA-event timers (gamd_profile_enable / gamd_profile_read)
@@ -139,10 +142,13 @@ int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cu
 int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st);
 int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int atoms_per_frame,
                           const float box[3], cudaStream_t st);
+int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64_t n_atoms, int atoms_per_frame,
+                const float box[3], cudaStream_t st);
+int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* feat, const int* orig_id,
                        int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st);
 
 int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
 int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
-int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt, int64_t n, double* ke_out, cudaStream_t st);
+int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt, int64_t n, double* ke_out, cudaStream_t st, int64_t n_own = -1);
 int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st);

@@ -32,13 +32,13 @@ __global__ void k_vv_second(double* __restrict__ v, const double* __restrict__ f
 }
 
 // pred (fp32, sorted order) -> f (fp64, caller order) [+ second half-kick] [+ kinetic energy]
-__global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __restrict__ perm, int64_t n,
+__global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __restrict__ perm, int64_t n, int64_t n_own,
                                  double sigma, double mean, double* __restrict__ f, double* __restrict__ v,
                                  const double* __restrict__ mass, double dt, double* __restrict__ ke) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double local = 0.0;
-  if (s < n) {
-    int64_t i = perm ? perm[s] : s;
+  int64_t i = s < n ? (perm ? perm[s] : s) : n_own;
+  if (i < n_own) {   // rows of halo atoms (caller index >= n_own) carry no force
     double m = v ? mass[i] : 1.0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -82,10 +82,11 @@ int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* m
 }
 
 int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt,
-                         int64_t n, double* ke_out, cudaStream_t st) {
+                         int64_t n, double* ke_out, cudaStream_t st, int64_t n_own) {
+  if (n_own < 0) n_own = n;
   if (ke_out) GAMD_CUDA(cudaMemsetAsync(ke_out, 0, sizeof(double), st));
   prof_mark(ctx, "integrate", st);
-  k_denorm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(ctx->pred, perm, n, sqrt(ctx->scaler_var), ctx->scaler_mean,
+  k_denorm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(ctx->pred, perm, n, n_own, sqrt(ctx->scaler_var), ctx->scaler_mean,
                                                      f_out, v, mass, dt, ke_out);
   GAMD_LAUNCH_CHECK();
   prof_mark(ctx, "integrate", st);

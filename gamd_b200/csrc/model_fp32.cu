@@ -524,9 +524,7 @@ int set_smem(gamd_ctx* ctx, K kernel) {
 
 }  // namespace
 
-int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*feat*/, const int* orig_id,
-                       int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st) {
-  const ModelW& mw = ctx->mw;
+static int model_attrs(gamd_ctx* ctx) {
   static bool attr_done = false;
   if (!attr_done) {
     int rc;
@@ -537,60 +535,93 @@ int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*fea
     if ((rc = set_smem(ctx, k_node_update<false, true>))) return rc;
     attr_done = true;
   }
+  return 0;
+}
+
+static NodeArgs node_args(const ModelW& mw) {
+  NodeArgs na{};
+  na.dec0_t = mw.dec0_t; na.dec0_b = mw.dec0_b; na.dec2_w = mw.dec2_w; na.dec2_b = mw.dec2_b;
+  na.node_emb = mw.node_emb; na.nenc_w = mw.nenc_w; na.nenc_b = mw.nenc_b;
+  return na;
+}
+
+// edge encoder + layer-0 node prologue (h0, LN_0, src/dst/phi_dst affines) for n_atoms rows
+int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64_t n_atoms, int atoms_per_frame,
+                const float box[3], cudaStream_t st) {
+  int rc = model_attrs(ctx);
+  if (rc) return rc;
+  const ModelW& mw = ctx->mw;
   const int grid_edge = ctx->sm_count * 3;
   const int node_tiles = ceil_div(n_atoms, TM);
   const int grid_node = node_tiles < ctx->sm_count * 3 ? node_tiles : ctx->sm_count * 3;
   const size_t smem = sizeof(Smem);
-
-  EncArgs ea{mw.enc0_t, mw.enc0_b, mw.enc2_t, mw.enc2_b, mw.enc4_t, mw.enc4_b, mw.eln_w, mw.eln_b, mw.centers,
-             mw.length_mean, mw.length_std, mw.n_edge_in, mw.use_bond, mw.expand_edge, {box[0], box[1], box[2]}};
-  prof_mark(ctx, "edge_encode", st);
   const bool tcpath = ctx->desc.precision != GAMD_PREC_FP32;
   const int agg_tile = tcpath ? 32 : GAMD_EDGE_TILE;
+  prof_mark(ctx, "edge_encode", st);
   if (tcpath) {
-    int rc = edge_encode_tc_launch(ctx, pos_feat, orig_id, atoms_per_frame, box, st);
-    if (rc) return rc;
+    if ((rc = edge_encode_tc_launch(ctx, pos_feat, orig_id, atoms_per_frame, box, st))) return rc;
   } else {
+    EncArgs ea{mw.enc0_t, mw.enc0_b, mw.enc2_t, mw.enc2_b, mw.enc4_t, mw.enc4_b, mw.eln_w, mw.eln_b, mw.centers,
+               mw.length_mean, mw.length_std, mw.n_edge_in, mw.use_bond, mw.expand_edge, {box[0], box[1], box[2]}};
     k_edge_encode<<<grid_edge, NT, smem, st>>>(ea, pos_feat, ctx->col_idx, ctx->edge_dst, ctx->n_edges, orig_id,
                                                ctx->d_bond, atoms_per_frame, ctx->e_emb, nullptr);
     GAMD_LAUNCH_CHECK();
   }
   prof_mark(ctx, "edge_encode", st);
-
-  NodeArgs na{};
-  na.dec0_t = mw.dec0_t; na.dec0_b = mw.dec0_b; na.dec2_w = mw.dec2_w; na.dec2_b = mw.dec2_b;
-  na.node_emb = mw.node_emb; na.nenc_w = mw.nenc_w; na.nenc_b = mw.nenc_b;
+  NodeArgs na = node_args(mw);
   na.next = mw.layer[0];
   prof_mark(ctx, "node_update", st);
-  k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg, ctx->part,
-                                                          ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd, ctx->pred);
+  k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
+                                                          ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd,
+                                                          ctx->pred);
   GAMD_LAUNCH_CHECK();
   prof_mark(ctx, "node_update", st);
-  for (int l = 0; l < mw.n_layers; l++) {
-    prof_mark(ctx, "mp_edge", st);
-    if (tcpath) {
-      int rc = mp_edge_tc_launch(ctx, l, st);
-      if (rc) return rc;
-    } else {
-      k_mp_edge<<<grid_edge, NT, smem, st>>>(mw.layer[l], ctx->e_emb, ctx->row_ptr, ctx->col_idx, ctx->edge_dst,
-                                             ctx->n_edges, ctx->hn, ctx->srcA, ctx->dstA, ctx->agg, ctx->part);
-      GAMD_LAUNCH_CHECK();
-    }
-    prof_mark(ctx, "mp_edge", st);
-    prof_mark(ctx, "node_update", st);
-    na.cur = mw.layer[l];
-    if (l + 1 < mw.n_layers) {
-      na.next = mw.layer[l + 1];
-      k_node_update<false, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
-                                                               ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA,
-                                                               ctx->pd, ctx->pred);
-    } else {
-      k_node_update<false, true><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
-                                                              ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA,
-                                                              ctx->pd, ctx->pred);
-    }
+  return 0;
+}
+
+// message-passing layer l: edge chain + segmented sum, then the node update (next layer's LN + affines, or the
+// force decoder after the last layer)
+int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st) {
+  const ModelW& mw = ctx->mw;
+  const int grid_edge = ctx->sm_count * 3;
+  const int node_tiles = ceil_div(n_atoms, TM);
+  const int grid_node = node_tiles < ctx->sm_count * 3 ? node_tiles : ctx->sm_count * 3;
+  const size_t smem = sizeof(Smem);
+  const bool tcpath = ctx->desc.precision != GAMD_PREC_FP32;
+  const int agg_tile = tcpath ? 32 : GAMD_EDGE_TILE;
+  prof_mark(ctx, "mp_edge", st);
+  if (tcpath) {
+    int rc = mp_edge_tc_launch(ctx, l, st);
+    if (rc) return rc;
+  } else {
+    k_mp_edge<<<grid_edge, NT, smem, st>>>(mw.layer[l], ctx->e_emb, ctx->row_ptr, ctx->col_idx, ctx->edge_dst,
+                                           ctx->n_edges, ctx->hn, ctx->srcA, ctx->dstA, ctx->agg, ctx->part);
     GAMD_LAUNCH_CHECK();
-    prof_mark(ctx, "node_update", st);
   }
+  prof_mark(ctx, "mp_edge", st);
+  prof_mark(ctx, "node_update", st);
+  NodeArgs na = node_args(mw);
+  na.cur = mw.layer[l];
+  if (l + 1 < mw.n_layers) {
+    na.next = mw.layer[l + 1];
+    k_node_update<false, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
+                                                             ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd,
+                                                             ctx->pred);
+  } else {
+    k_node_update<false, true><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
+                                                            ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd,
+                                                            ctx->pred);
+  }
+  GAMD_LAUNCH_CHECK();
+  prof_mark(ctx, "node_update", st);
+  return 0;
+}
+
+int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*feat*/, const int* orig_id,
+                       int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st) {
+  int rc = model_begin(ctx, pos_feat, orig_id, n_atoms, atoms_per_frame, box, st);
+  if (rc) return rc;
+  for (int l = 0; l < ctx->mw.n_layers; l++)
+    if ((rc = model_layer(ctx, l, pos_feat, n_atoms, st))) return rc;
   return 0;
 }

@@ -307,7 +307,7 @@ __global__ void k_gather_sorted(const uint32_t* __restrict__ keys, const uint32_
                                 int ncells, const float4* __restrict__ pos_nbr, const float4* __restrict__ pos_feat,
                                 const float* __restrict__ feat, float4* __restrict__ pos_nbr_s,
                                 float4* __restrict__ pos_feat_s, int* __restrict__ perm,
-                                int* __restrict__ cell_start) {
+                                int* __restrict__ inv_perm, int* __restrict__ cell_start) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   int i = (int)vals[s];
@@ -316,6 +316,7 @@ __global__ void k_gather_sorted(const uint32_t* __restrict__ keys, const uint32_
   pf.w = feat ? feat[i] : 0.f;
   pos_feat_s[s] = pf;
   perm[s] = i;
+  inv_perm[i] = s;
   int k = (int)keys[s];
   int kp = s > 0 ? (int)keys[s - 1] : -1;
   for (int c = kp + 1; c <= k; c++) cell_start[c] = s;
@@ -368,6 +369,10 @@ __global__ void __launch_bounds__(256) k_sweep(NbrParams p, const float4* __rest
   int cx = c % p.nc[0];
   int cy = (c / p.nc[0]) % p.nc[1];
   int cz = c / (p.nc[0] * p.nc[1]);
+  if (__float_as_int(pc.w) >= p.n_centers) {   // halo atom: neighbour only
+    if (!WRITE && lane == 0) deg[s] = 0;
+    return;
+  }
   int base = WRITE ? row_ptr[s] : 0;
   if (WRITE && row_ptr[s + 1] > cap) {
     if (lane == 0) atomicOr(err_flag, 1);
@@ -454,6 +459,7 @@ int nbr_setup_params(gamd_ctx* ctx, int64_t n_atoms, int n_frames, const float b
   // python: `dr_2 < cutoff ** 2` - the square is taken in double, then rounded to fp32
   p->rc2 = (float)((double)rc * (double)rc);
   p->flags = flags;
+  p->n_centers = (int)n_atoms;
   return 0;
 }
 
@@ -485,7 +491,7 @@ int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, c
   }
   k_gather_sorted<<<ceil_div(n, 256), 256, 0, st>>>(ctx->keys[buf], ctx->vals[buf], n, (int)ncells, ctx->pos_nbr,
                                                     ctx->pos_feat, d_feat, ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm,
-                                                    ctx->cell_start);
+                                                    ctx->inv_perm, ctx->cell_start);
   GAMD_LAUNCH_CHECK();
   int cap = (int)ctx->cap_edges;
   int blocks = ceil_div((int64_t)n * 32, 256);

@@ -172,6 +172,25 @@ int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, cons
                       int64_t n_atoms, int32_t n_frames, const double h_box[3], float cutoff,
                       const float* h_feat, double dt);
 
+/* ---- spatial domain decomposition (multi-GPU, one ctx per rank) ------------------------------- */
+/* The reference has no counterpart (its MD loop is single-GPU); these entry points
+ * split gamd_compute_forces at the points where a rank needs data of atoms it does not own:
+ *   gamd_dd_begin   local atoms = n_own owned + (n_local - n_own) halo atoms (neighbours only: no CSR row);
+ *                   neighbor search with the GLOBAL periodic box, edge encoder, layer-0 node prologue
+ *   gamd_dd_layer   message-passing layer `layer` + node update (decoder after the last layer)
+ *   gamd_dd_pack_rows / gamd_dd_unpack_rows   rows [hn | src_affine(hn)] (2 x 128 fp32) of the listed owned
+ *                   atoms -> send buffer; received rows -> the halo atoms first_local_idx .. +n-1.  The caller
+ *                   moves the buffers between ranks (NCCL send/recv over NVLink) after layers 0 .. L-2.
+ *   gamd_dd_finish  de-normalised forces of the owned atoms (local order) [+ second half-kick, + kinetic energy]
+ * d_pos fp64 [n_local,3] Angstrom, owned atoms first. */
+int gamd_dd_begin(gamd_ctx* ctx, const double* d_pos, int64_t n_own, int64_t n_local, const double h_box[3],
+                  float cutoff, const float* d_feat, void* stream);
+int gamd_dd_layer(gamd_ctx* ctx, int32_t layer, void* stream);
+int gamd_dd_pack_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, float* d_out, void* stream);
+int gamd_dd_unpack_rows(gamd_ctx* ctx, int64_t first_local_idx, int64_t n, const float* d_in, void* stream);
+int gamd_dd_finish(gamd_ctx* ctx, double* d_force, double* d_v, const double* d_mass, double dt, double* d_ke,
+                   void* stream);
+
 /* synchronises `stream` and reports errors raised asynchronously on the device since the
  * last check (GAMD_ECAPACITY: edge capacity exceeded; GAMD_EINVAL: edge list not sorted by
  * centre or ids out of range).  The *_host entry points call it themselves. */
