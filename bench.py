@@ -186,14 +186,82 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     prec = {"fp32": _capi.PREC_FP32, "bf16x3": _capi.PREC_BF16X3, "bf16": _capi.PREC_BF16}[args.precision]
 
-    # every rank runs its own replica of the workload (no collective on the data path)
-    pos, box, rc, m, scaler, kind, temp = build_system(args.workload, seed=42 + rank)
-    n = len(pos)
-    s = np.load(os.path.join(FIX, scaler))
-    sd = random_state_dict(0, kind=kind)
-    eng = MDEngine(kind, sd, box, rc, m, s["mean"], s["var"], precision=prec, device=local)
-    eng.set_state(pos / 10.0, maxwell_boltzmann(m, temp, 1234 + rank))
-    n_edges = eng.ctx.neighbor_count()
+    s_np = None
+    mode = args.parallel
+    if mode == "auto":
+        mode = "dd" if (world > 1 and WORKLOADS[args.workload]["n_side"]) else "replicas"
+    if mode == "dd":
+        # spatial domain decomposition (strong scaling): ONE box, slabs along x, NCCL halo exchange per layer
+        from gamd_b200.dist import CudaBackend, SlabDomainMD, SlabPlan
+        pos, box, rc, m, scaler, kind, temp = build_system(args.workload, seed=42)
+        s_np = np.load(os.path.join(FIX, scaler))
+        n_total = len(pos)
+        ctx = _capi.Context(kind=_capi.MODEL_LJ, precision=prec, device=local)
+        ctx.load_state_dict(random_state_dict(0, kind=kind))
+        ctx.set_scaler(s_np["mean"], s_np["var"])
+        ctx.finalize()
+        plan = SlabPlan(box, rc, world, rank)
+        n_loc_cap = int((n_total / world) * (1.0 + 2.0 * plan.halo / plan.width) * 1.15) + 4096
+        ctx.reserve(n_loc_cap, int(n_total / world * 1.1 + 4096) * 34)
+        md = SlabDomainMD.scatter_global(CudaBackend(ctx, box, rc, 4), plan, pos / 10.0,
+                                         maxwell_boltzmann(m, temp, 1234), m, f"cuda:{local}")
+        md.compute_forces()
+        ctx.check_async_errors()
+        n = int(md.x.shape[0])
+        n_edges = ctx.neighbor_count()
+
+        def run_steps(k):
+            for _ in range(k):
+                md.step(DT)
+
+        def host_buffers():
+            return [torch.empty((md.x.shape[0] + 4096, 3), dtype=torch.float64).pin_memory() for _ in range(3)]
+
+        def step_host(bufs):
+            # host-buffer call shape of one rank: H2D of its x, v, f; step; D2H of x, v, f
+            k = md.x.shape[0]
+            md.x.copy_(bufs[0][:k], non_blocking=True)
+            md.v.copy_(bufs[1][:k], non_blocking=True)
+            md.f.copy_(bufs[2][:k], non_blocking=True)
+            md.step(DT)
+            k = md.x.shape[0]
+            bufs[0][:k].copy_(md.x, non_blocking=True)
+            bufs[1][:k].copy_(md.v, non_blocking=True)
+            bufs[2][:k].copy_(md.f, non_blocking=True)
+            torch.cuda.synchronize()
+
+        def fill_host(bufs):
+            k = md.x.shape[0]
+            bufs[0][:k].copy_(md.x); bufs[1][:k].copy_(md.v); bufs[2][:k].copy_(md.f)
+            torch.cuda.synchronize()
+        atoms_all = n_total
+        scaling = "strong"
+        api = "SlabDomainMD.step with pinned host x, v, f per rank"
+    else:
+        # every rank runs its own replica of the workload (no collective on the data path)
+        pos, box, rc, m, scaler, kind, temp = build_system(args.workload, seed=42 + rank)
+        n = len(pos)
+        s_np = np.load(os.path.join(FIX, scaler))
+        sd = random_state_dict(0, kind=kind)
+        eng = MDEngine(kind, sd, box, rc, m, s_np["mean"], s_np["var"], precision=prec, device=local)
+        eng.set_state(pos / 10.0, maxwell_boltzmann(m, temp, 1234 + rank))
+        ctx = eng.ctx
+        n_edges = ctx.neighbor_count()
+
+        def run_steps(k):
+            eng.step(k, DT)
+
+        def host_buffers():
+            return [torch.empty((n, 3), dtype=torch.float64).pin_memory() for _ in range(3)]
+
+        def fill_host(bufs):
+            bufs[0].copy_(eng.x.cpu()); bufs[1].copy_(eng.v.cpu()); bufs[2].copy_(eng.f.cpu())
+
+        def step_host(bufs):
+            eng.step_host(bufs[0].numpy(), bufs[1].numpy(), bufs[2].numpy(), DT)
+        atoms_all = world * n
+        scaling = "weak"
+        api = "MDEngine.step_host -> gamd_md_step_host (pinned host buffers)"
 
     def barrier():
         torch.cuda.synchronize()
@@ -202,41 +270,38 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident arm ----
-    eng.step(args.warmup, DT)
-    eng.ctx.check_async_errors()
-    eng.ctx.profile_enable(True)
+    run_steps(args.warmup)
+    ctx.check_async_errors()
+    ctx.profile_enable(True)
     for st in ("neighbor", "edge_encode", "mp_edge", "node_update", "integrate"):
-        eng.ctx.profile_read(st)
-    launches0 = eng.ctx.launch_count
+        ctx.profile_read(st)
+    launches0 = ctx.launch_count
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    eng.step(args.steps, DT)
+    run_steps(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = eng.ctx.launch_count - launches0
+    launches = ctx.launch_count - launches0
     clocks = sampler.stop() if sampler else None
-    eng.ctx.check_async_errors()
-    stages = {st: eng.ctx.profile_read(st) for st in ("neighbor", "edge_encode", "mp_edge", "node_update", "integrate")}
-    eng.ctx.profile_enable(False)
+    ctx.check_async_errors()
+    stages = {st: ctx.profile_read(st) for st in ("neighbor", "edge_encode", "mp_edge", "node_update", "integrate")}
+    ctx.profile_enable(False)
 
     # ---- end-to-end arm: host buffers, pinned, copies inside the timed region ----
-    xh = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    vh = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    fh = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    xh.copy_(eng.x.cpu()); vh.copy_(eng.v.cpu()); fh.copy_(eng.f.cpu())
-    xn, vn, fn = xh.numpy(), vh.numpy(), fh.numpy()
+    bufs = host_buffers()
+    fill_host(bufs)
     e2e_steps = max(1, min(args.steps, 5))
-    eng.step_host(xn, vn, fn, DT)
+    step_host(bufs)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.step_host(xn, vn, fn, DT)
+        step_host(bufs)
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = 3 * n * 24 + n * 8 + (n * 4 if kind == "water" else 0)
+    h2d = 3 * n * 24 + (n * 8 + (n * 4 if kind == "water" else 0) if mode != "dd" else 0)
     d2h = 3 * n * 24
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -253,17 +318,19 @@ def run_ours(args):
     mp_avg_s = mp_ms / max(mp_cnt, 1) * 1e-3
     flop_per_launch = 131072.0 * n_edges            # 4 x (128x128) mat-vec per edge
     achieved = flop_per_launch / mp_avg_s / 1e12 if mp_avg_s > 0 else 0.0
-    value = world * n * args.steps / (ms * 1e-3)
-    e2e_val = world * n * e2e_steps / (e2e_ms * 1e-3)
+    value = atoms_all * args.steps / (ms * 1e-3)
+    e2e_val = atoms_all * e2e_steps / (e2e_ms * 1e-3)
     line = {
         "metric": "atom-steps/s of GNN-force MD", "value": value, "unit": "atom-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (fp32 accumulate)",
+        "scaling": scaling, "vs_baseline": None, "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (fp32 accumulate)",
                                                           "bf16": "bf16 (fp32 accumulate)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "atoms_per_gpu": n,
                    "edges_per_gpu": n_edges, "model": "MDNet 128/128/128 x4 layers, random-init (numpy PCG64 seed 0)",
-                   "parallelism": "replicas" if world > 1 else "single", "precision": args.precision,
+                   "parallelism": ("slab domain decomposition x%d, NCCL halo exchange per MP layer" % world if mode == "dd"
+                                   else ("independent replicas x%d" % world if world > 1 else "single")),
+                   "atoms_total": atoms_all, "precision": args.precision,
                    "l2": "working set (edge embeddings %.1f GB) is larger than L2" % (n_edges * 512 / 1e9)
                    if n_edges * 512 > 2e8 else "working set fits L2 (latency-bound system)"},
         "edges_per_s_per_layer": n_edges / mp_avg_s if mp_avg_s > 0 else None,
@@ -278,7 +345,7 @@ def run_ours(args):
                      "hardware_tflops": achieved * (3 if args.precision == "bf16x3" else 1),
                      "hbm_frac": ((516.0 * n_edges + 1028.0 * n) / mp_avg_s / 1e9 / hbm_peak) if mp_avg_s > 0 else None},
         "e2e": {"value": e2e_val, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "MDEngine.step_host -> gamd_md_step_host (pinned host buffers)"},
+                "steps": e2e_steps, "api": api},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -306,6 +373,9 @@ def main():
                     help="arithmetic of the edge-sized GEMMs: bf16x3 = tcgen05 3-pass split-bf16 (meets the 1e-4 force "
                          "tolerance, default), bf16 = single pass (tolerance 1e-2), fp32 = CUDA-core FFMA parity anchor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="auto", choices=["auto", "dd", "replicas"],
+                    help="N > 1: dd = slab domain decomposition of ONE box (strong scaling, default for the LJ boxes), "
+                         "replicas = one independent system per rank (weak scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
