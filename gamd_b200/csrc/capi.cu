@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 static std::string g_create_err;
 
@@ -94,6 +95,7 @@ void carve(gamd_ctx* ctx, Carver& c, int64_t A, int64_t E) {
   ctx->row_ptr_o = c.take<int>(A + 1);
   ctx->n_edges = c.take<int>(4);
   ctx->err_flag = c.take<int>(4);
+  ctx->d_stepctr = c.take<int>(4);
   ctx->col_idx = c.take<int>(E);
   ctx->edge_dst = c.take<int>(E);
   ctx->e_emb = c.take<float>((size_t)(E + 256) * GAMD_NF);   // fp32 rows, or 64 KB bf16 hi/lo blobs per 128-edge tile
@@ -229,6 +231,7 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   gamd_ctx* ctx = new gamd_ctx();
   ctx->device = device;
   ctx->desc = *desc;
+  ctx->use_graphs = getenv("GAMD_NO_GRAPH") == nullptr;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   *out = ctx;
@@ -246,6 +249,10 @@ int gamd_destroy(gamd_ctx* ctx) {
   if (ctx->d_tc_bias_enc) cudaFree(ctx->d_tc_bias_enc);
   if (ctx->d_bond) cudaFree(ctx->d_bond);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  if (ctx->graph_stream) cudaStreamDestroy(ctx->graph_stream);
+  if (ctx->graph_ev_in) cudaEventDestroy(ctx->graph_ev_in);
+  if (ctx->graph_ev_out) cudaEventDestroy(ctx->graph_ev_out);
   delete ctx;
   return 0;
 }
@@ -287,6 +294,7 @@ int gamd_reserve(gamd_ctx* ctx, int64_t max_atoms, int64_t max_edges) {
     ctx->pinned_bytes = 0;
   }
   ctx->last_nbr = NbrParams{};
+  ctx->graph_key = 0;
   return 0;
 }
 
@@ -313,6 +321,7 @@ int gamd_set_scaler(gamd_ctx* ctx, double mean, double var) {
   if (!ctx || !(var >= 0.0)) return GAMD_EINVAL;
   ctx->scaler_mean = mean;
   ctx->scaler_var = var;
+  ctx->graph_key = 0;   // the scaler is baked into captured kernel arguments
   return 0;
 }
 
@@ -347,6 +356,7 @@ int gamd_set_bonds(gamd_ctx* ctx, const int64_t* h_bonds, int64_t nb, int64_t n_
   GAMD_CUDA(cudaMalloc(&ctx->d_bond, tab.size() * sizeof(int)));
   GAMD_CUDA(cudaMemcpy(ctx->d_bond, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
   ctx->bond_atoms = n_atoms_per_frame;
+  ctx->graph_key = 0;
   return 0;
 }
 
@@ -518,6 +528,7 @@ int gamd_finalize_weights(gamd_ctx* ctx) {
     }
   }
   ctx->finalized = true;
+  ctx->graph_key = 0;
   return 0;
 }
 
@@ -653,13 +664,83 @@ int gamd_md_run(gamd_ctx* ctx, double* d_x, double* d_v, double* d_f, const doub
     return GAMD_EINVAL;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  for (int s = 0; s < n_steps; s++) {
-    if ((rc = integ_first_half(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, st))) return rc;
+  if (n_steps == 0) return 0;
+  if (d_ke) GAMD_CUDA(cudaMemsetAsync(d_ke, 0, sizeof(double) * n_steps, st));
+  GAMD_CUDA(cudaMemsetAsync(ctx->d_stepctr, 0, sizeof(int), st));
+  auto one_step = [&](cudaStream_t s_) -> int {
+    int r;
+    if ((r = integ_first_half(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, s_))) return r;
     // forces at x*10 Angstrom (test_nosehoover.py:112: value_in_unit(angstrom))
-    if ((rc = positions_to_forces(ctx, d_x, 10.0, n_atoms, n_frames, h_box, cutoff, d_feat, st))) return rc;
-    if ((rc = integ_denorm_scatter(ctx, ctx->perm, d_f, d_v, d_mass, dt, n_atoms, d_ke ? d_ke + s : nullptr, st)))
-      return rc;
+    if ((r = positions_to_forces(ctx, d_x, 10.0, n_atoms, n_frames, h_box, cutoff, d_feat, s_))) return r;
+    if ((r = integ_denorm_scatter(ctx, ctx->perm, d_f, d_v, d_mass, dt, n_atoms, d_ke, s_, -1, ctx->d_stepctr))) return r;
+    return d_ke ? integ_inc_counter(ctx, ctx->d_stepctr, s_) : 0;
+  };
+  // the first step always runs eagerly (it also sets the one-time kernel attributes)
+  const int64_t l0 = ctx->launches;
+  if ((rc = one_step(st))) return rc;
+  ctx->launches_last_step = ctx->launches - l0;
+  int done = 1;
+  // launch-bound systems: capture one step into a CUDA graph and replay it (every grid is shape-static: tile
+  // loops read the edge count from device memory).  Large systems gain nothing and keep the eager path.
+  const bool graph_ok = ctx->use_graphs && !ctx->prof_on && n_steps >= 4 && n_atoms <= 200000;
+  if (graph_ok) {
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+    mix((uint64_t)d_x); mix((uint64_t)d_v); mix((uint64_t)d_f); mix((uint64_t)d_mass); mix((uint64_t)d_feat);
+    mix((uint64_t)d_ke); mix((uint64_t)n_atoms); mix((uint64_t)n_frames); mix((uint64_t)ctx->arena);
+    uint64_t bits;
+    for (int d = 0; d < 3; d++) { memcpy(&bits, &h_box[d], 8); mix(bits); }
+    memcpy(&bits, &dt, 8); mix(bits);
+    uint32_t cb; memcpy(&cb, &cutoff, 4); mix(cb);
+    mix((uint64_t)ctx->scaler_var * 0 + (uint64_t)ctx->finalized);
+    if (!ctx->graph_stream) {
+      GAMD_CUDA(cudaStreamCreateWithFlags(&ctx->graph_stream, cudaStreamNonBlocking));
+      GAMD_CUDA(cudaEventCreateWithFlags(&ctx->graph_ev_in, cudaEventDisableTiming));
+      GAMD_CUDA(cudaEventCreateWithFlags(&ctx->graph_ev_out, cudaEventDisableTiming));
+    }
+    if (key != ctx->graph_key || !ctx->graph_exec) {
+      if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+      ctx->graph_exec = nullptr;
+      ctx->graph_key = 0;
+      cudaGraph_t graph = nullptr;
+      const int64_t launches0 = ctx->launches;
+      GAMD_CUDA(cudaStreamBeginCapture(ctx->graph_stream, cudaStreamCaptureModeThreadLocal));
+      rc = one_step(ctx->graph_stream);
+      cudaError_t ce = cudaStreamEndCapture(ctx->graph_stream, &graph);
+      ctx->launches = launches0;   // captured, not launched
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (ce != cudaSuccess) {
+        ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
+        return GAMD_ECUDA;
+      }
+      ce = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        ctx->graph_exec = nullptr;
+        ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce);
+        return GAMD_ECUDA;
+      }
+      ctx->graph_key = key;
+      ctx->graph_launches_per_step = 0;
+    }
+    if (!ctx->graph_launches_per_step) {
+      // kernels per replayed step = what one eager step issued (for gamd_launch_count bookkeeping)
+      ctx->graph_launches_per_step = ctx->launches_last_step;
+    }
+    GAMD_CUDA(cudaEventRecord(ctx->graph_ev_in, st));
+    GAMD_CUDA(cudaStreamWaitEvent(ctx->graph_stream, ctx->graph_ev_in, 0));
+    for (; done < n_steps; done++) {
+      GAMD_CUDA(cudaGraphLaunch(ctx->graph_exec, ctx->graph_stream));
+      ctx->launches += ctx->graph_launches_per_step;
+    }
+    GAMD_CUDA(cudaEventRecord(ctx->graph_ev_out, ctx->graph_stream));
+    GAMD_CUDA(cudaStreamWaitEvent(st, ctx->graph_ev_out, 0));
   }
+  for (; done < n_steps; done++)
+    if ((rc = one_step(st))) return rc;
   return 0;
 }
 

@@ -93,6 +93,14 @@ struct gamd_ctx {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   NbrParams last_nbr{};
+  // CUDA-graph replay of the MD step (launch-bound small systems)
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_key = 0;
+  cudaStream_t graph_stream = nullptr;
+  cudaEvent_t graph_ev_in = nullptr, graph_ev_out = nullptr;
+  int* d_stepctr = nullptr;
+  bool use_graphs = true;
+  int64_t graph_launches_per_step = 0, launches_last_step = 0;
   int64_t dd_n_own = 0, dd_n_loc = 0;   // domain decomposition: owned / owned + halo atoms of the step in flight
   int sm_count = 148;
 
@@ -150,5 +158,6 @@ int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* feat,
 
 int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
 int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
-int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt, int64_t n, double* ke_out, cudaStream_t st, int64_t n_own = -1);
+int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt, int64_t n, double* ke_out, cudaStream_t st, int64_t n_own = -1, const int* ke_slot = nullptr);
+int integ_inc_counter(gamd_ctx* ctx, int* counter, cudaStream_t st);
 int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st);

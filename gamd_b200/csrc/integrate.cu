@@ -34,7 +34,8 @@ __global__ void k_vv_second(double* __restrict__ v, const double* __restrict__ f
 // pred (fp32, sorted order) -> f (fp64, caller order) [+ second half-kick] [+ kinetic energy]
 __global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __restrict__ perm, int64_t n, int64_t n_own,
                                  double sigma, double mean, double* __restrict__ f, double* __restrict__ v,
-                                 const double* __restrict__ mass, double dt, double* __restrict__ ke) {
+                                 const double* __restrict__ mass, double dt, double* __restrict__ ke,
+                                 const int* __restrict__ ke_slot) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double local = 0.0;
   int64_t i = s < n ? (perm ? perm[s] : s) : n_own;
@@ -60,7 +61,7 @@ __global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __re
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sw[w];
-      atomicAdd(ke, t);
+      atomicAdd(ke + (ke_slot ? *ke_slot : 0), t);
     }
   }
 }
@@ -82,13 +83,22 @@ int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* m
 }
 
 int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt,
-                         int64_t n, double* ke_out, cudaStream_t st, int64_t n_own) {
+                         int64_t n, double* ke_out, cudaStream_t st, int64_t n_own, const int* ke_slot) {
   if (n_own < 0) n_own = n;
-  if (ke_out) GAMD_CUDA(cudaMemsetAsync(ke_out, 0, sizeof(double), st));
+  // ke_slot != nullptr: ke_out is a per-step trace zeroed by the caller, *ke_slot selects the entry (CUDA-graph replay)
+  if (ke_out && !ke_slot) GAMD_CUDA(cudaMemsetAsync(ke_out, 0, sizeof(double), st));
   prof_mark(ctx, "integrate", st);
   k_denorm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(ctx->pred, perm, n, n_own, sqrt(ctx->scaler_var), ctx->scaler_mean,
-                                                     f_out, v, mass, dt, ke_out);
+                                                     f_out, v, mass, dt, ke_out, ke_slot);
   GAMD_LAUNCH_CHECK();
   prof_mark(ctx, "integrate", st);
+  return 0;
+}
+
+__global__ void k_inc_counter(int* c) { *c += 1; }
+
+int integ_inc_counter(gamd_ctx* ctx, int* counter, cudaStream_t st) {
+  k_inc_counter<<<1, 1, 0, st>>>(counter);
+  GAMD_LAUNCH_CHECK();
   return 0;
 }
