@@ -39,6 +39,8 @@ WORKLOADS = {
     "lj32k": dict(kind="lj", n_side=32, desc="LJ box 32,768 atoms, same density/cutoff"),
     "lj258": dict(kind="lj", n_side=None, desc="LJ argon 258 atoms (configs[0] fixture)"),
     "tip3p774": dict(kind="water", n_side=None, desc="TIP3P 258 molecules / 774 atoms (configs[1] fixture)"),
+    "tip4p4096": dict(kind="water", n_side=None, desc="TIP4P-Ew 4096 molecules, 16384 sites, 12288 GNN nodes, "
+                                                         "virtual M site re-placed every step (configs[2])"),
 }
 FIX = os.path.join(ROOT, "tests", "golden", "fixtures")
 DT = 0.002  # ps (test_nosehoover.py:29)
@@ -55,6 +57,12 @@ def build_system(name, seed=42):
         pos = np.load(os.path.join(FIX, "water_init_pos.npy")).astype(np.float64)
         m = np.tile([15.999, 1.008, 1.008], len(pos) // 3)
         return pos, 20.0, 4.2, m, "scaler_tip3p.npz", "water", 300.0
+    if name == "tip4p4096":
+        from gamd_b200.engine import synthetic_tip4p_box
+        x4, L = synthetic_tip4p_box(16, seed=7)
+        pos = x4[np.arange(len(x4)) % 4 < 3]              # the GNN sees O, H, H (code/train_utils.py:58-64)
+        m = np.tile([15.9994, 1.008, 1.008], len(pos) // 3)
+        return pos, L, 4.2, m, "scaler_tip4p.npz", "water", 300.0
     pos, L = synthetic_lj_box(w["n_side"], seed=seed)
     return pos, L, 7.5, np.full(len(pos), 39.9), "scaler_lj.npz", "lj", 100.0
 
@@ -243,13 +251,27 @@ def run_ours(args):
         n = len(pos)
         s_np = np.load(os.path.join(FIX, scaler))
         sd = random_state_dict(0, kind=kind)
-        eng = MDEngine(kind, sd, box, rc, m, s_np["mean"], s_np["var"], precision=prec, device=local)
-        eng.set_state(pos / 10.0, maxwell_boltzmann(m, temp, 1234 + rank))
+        tip4p = None
+        if args.workload == "tip4p4096":
+            from gamd_b200.engine import TIP4PEngine, synthetic_tip4p_box
+            x4, _ = synthetic_tip4p_box(16, seed=7)
+            tip4p = TIP4PEngine(sd, box, rc, n // 3, s_np["mean"], s_np["var"], precision=prec, device=local)
+            v4 = np.zeros_like(x4)
+            v4[np.arange(len(x4)) % 4 < 3] = maxwell_boltzmann(m, temp, 1234 + rank)
+            tip4p.set_state(x4 / 10.0, v4)
+            eng = tip4p.eng
+        else:
+            eng = MDEngine(kind, sd, box, rc, m, s_np["mean"], s_np["var"], precision=prec, device=local)
+            eng.set_state(pos / 10.0, maxwell_boltzmann(m, temp, 1234 + rank))
         ctx = eng.ctx
         n_edges = ctx.neighbor_count()
 
         def run_steps(k):
-            eng.step(k, DT)
+            if tip4p is not None:
+                for _ in range(k):
+                    tip4p.step(1, DT)          # M site re-placed after every step
+            else:
+                eng.step(k, DT)
 
         def host_buffers():
             return [torch.empty((n, 3), dtype=torch.float64).pin_memory() for _ in range(3)]

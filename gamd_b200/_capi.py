@@ -59,6 +59,8 @@ SIGNATURES = {
                               c_float, c_void_p, c_double, c_int32, c_void_p, c_void_p]),
     "gamd_md_step_host": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                     POINTER(c_double), c_float, c_void_p, c_double]),
+    "gamd_tip4p_strip": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gamd_tip4p_unstrip": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_void_p]),
     "gamd_dd_begin": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_double), c_float, c_void_p, c_void_p]),
     "gamd_dd_layer": (c_int32, [c_void_p, c_int32, c_void_p]),
     "gamd_dd_pack_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -230,6 +232,13 @@ class Context:
     def md_step_host(self, x, v, f, mass, box, cutoff, dt, feat=None, n_frames=1):
         self._check(self.lib.gamd_md_step_host(self._h, _ptr(x), _ptr(v), _ptr(f), _ptr(mass), x.shape[0], n_frames,
                                                _box3(box), float(cutoff), _ptr(feat), float(dt)))
+
+    def tip4p_strip(self, x4, x3):
+        self._check(self.lib.gamd_tip4p_strip(self._h, _ptr(x4), _ptr(x3), x4.shape[0] // 4, _stream()))
+
+    def tip4p_unstrip(self, a3, a4, w_o, w_h, place_m):
+        self._check(self.lib.gamd_tip4p_unstrip(self._h, _ptr(a3), _ptr(a4), a4.shape[0] // 4, float(w_o), float(w_h),
+                                                int(place_m), _stream()))
 
     # ---- domain decomposition ----
     def dd_begin(self, pos_f64, n_own, box, cutoff, feat=None):

@@ -770,6 +770,17 @@ int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, cons
   return gamd_check_async_errors(ctx, st);
 }
 
+int gamd_tip4p_strip(gamd_ctx* ctx, const double* d_x4, double* d_x3, int64_t n_mol, void* stream) {
+  if (!ctx || !d_x4 || !d_x3 || n_mol <= 0) return GAMD_EINVAL;
+  return integ_tip4p_strip(ctx, d_x4, d_x3, n_mol, (cudaStream_t)stream);
+}
+
+int gamd_tip4p_unstrip(gamd_ctx* ctx, const double* d_a3, double* d_a4, int64_t n_mol, double w_o, double w_h,
+                       int32_t place_m, void* stream) {
+  if (!ctx || !d_a3 || !d_a4 || n_mol <= 0) return GAMD_EINVAL;
+  return integ_tip4p_unstrip(ctx, d_a3, d_a4, n_mol, w_o, w_h, place_m, (cudaStream_t)stream);
+}
+
 int gamd_dd_begin(gamd_ctx* ctx, const double* d_pos, int64_t n_own, int64_t n_local, const double h_box[3],
                   float cutoff, const float* d_feat, void* stream) {
   int rc = check_ready(ctx);

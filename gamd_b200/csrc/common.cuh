@@ -160,4 +160,6 @@ int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const
 int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
 int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt, int64_t n, double* ke_out, cudaStream_t st, int64_t n_own = -1, const int* ke_slot = nullptr);
 int integ_inc_counter(gamd_ctx* ctx, int* counter, cudaStream_t st);
+int integ_tip4p_strip(gamd_ctx* ctx, const double* x4, double* x3, int64_t n_mol, cudaStream_t st);
+int integ_tip4p_unstrip(gamd_ctx* ctx, const double* a3, double* a4, int64_t n_mol, double wo, double wh, int place_m, cudaStream_t st);
 int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st);

@@ -102,3 +102,40 @@ int integ_inc_counter(gamd_ctx* ctx, int* counter, cudaStream_t st) {
   GAMD_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- TIP4P virtual sites -------------------------------------------------
+// 4-site molecules [O, H, H, M]: the model sees only O, H, H (code/train_utils.py:58-64: arange % 4 < 3);
+// the massless M site is re-placed from them (OpenMM "average3" virtual site).
+__global__ void k_tip4p_strip(const double* __restrict__ x4, double* __restrict__ x3, int64_t n_mol) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (molecule, site<3, component)
+  if (i >= n_mol * 9) return;
+  int64_t mol = i / 9;
+  int r = (int)(i - mol * 9);
+  x3[i] = x4[mol * 12 + r];
+}
+
+__global__ void k_tip4p_unstrip(const double* __restrict__ a3, double* __restrict__ a4, int64_t n_mol, double wo,
+                                double wh, int place_m) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (molecule, component)
+  if (i >= n_mol * 3) return;
+  int64_t mol = i / 3;
+  int k = (int)(i - mol * 3);
+  double o = a3[mol * 9 + k], h1 = a3[mol * 9 + 3 + k], h2 = a3[mol * 9 + 6 + k];
+  a4[mol * 12 + k] = o;
+  a4[mol * 12 + 3 + k] = h1;
+  a4[mol * 12 + 6 + k] = h2;
+  a4[mol * 12 + 9 + k] = place_m ? wo * o + wh * h1 + wh * h2 : 0.0;
+}
+
+int integ_tip4p_strip(gamd_ctx* ctx, const double* x4, double* x3, int64_t n_mol, cudaStream_t st) {
+  k_tip4p_strip<<<ceil_div(n_mol * 9, 256), 256, 0, st>>>(x4, x3, n_mol);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int integ_tip4p_unstrip(gamd_ctx* ctx, const double* a3, double* a4, int64_t n_mol, double wo, double wh, int place_m,
+                        cudaStream_t st) {
+  k_tip4p_unstrip<<<ceil_div(n_mol * 3, 256), 256, 0, st>>>(a3, a4, n_mol, wo, wh, place_m);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}

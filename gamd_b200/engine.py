@@ -105,3 +105,68 @@ class MDEngine:
 
     def close(self):
         self.ctx.close()
+
+
+TIP4PEW_WEIGHTS = (0.786646558, 0.106676721)   # average3 weights of the TIP4P-Ew M site (O, each H)
+
+
+def synthetic_tip4p_box(n_side, seed=7, density=251 / 20.0 ** 3):
+    """n_side^3 rigid TIP4P-Ew molecules [O,H,H,M] (O-H 0.9572 A, HOH 104.52 deg) with random orientations on a
+    jittered cubic lattice at the reference density 251 molecules / (20 A)^3.
+    Returns (positions A [4*n_mol,3], box A)."""
+    n_mol = n_side ** 3
+    L = (n_mol / density) ** (1.0 / 3.0)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = (np.arange(n_side) + 0.5) * (L / n_side)
+    c = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3) + 0.15 * rng.standard_normal((n_mol, 3))
+    th = np.deg2rad(104.52) / 2
+    local = np.array([[0, 0, 0], [0.9572 * np.sin(th), 0, 0.9572 * np.cos(th)], [-0.9572 * np.sin(th), 0, 0.9572 * np.cos(th)]])
+    q = rng.standard_normal((n_mol, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                  np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                  np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], 1)
+    ohh = c[:, None, :] + np.einsum("mij,sj->msi", R, local)
+    wo, wh = TIP4PEW_WEIGHTS
+    msite = wo * ohh[:, 0] + wh * (ohh[:, 1] + ohh[:, 2])
+    return np.concatenate([ohh, msite[:, None]], axis=1).reshape(-1, 3), float(L)
+
+
+class TIP4PEngine:
+    """4-site water [O,H,H,M] on top of ``MDEngine``: the GNN sees and integrates only the massive O,H,H sites
+    (code/train_utils.py:58-64); after every batch of steps the massless M site is re-placed from them and
+    carries zero force and velocity."""
+
+    def __init__(self, sd, box, cutoff, n_mol, scaler_mean=0.0, scaler_var=1.0, precision=_capi.PREC_BF16X3, device=0):
+        masses = np.tile([15.9994, 1.008, 1.008], n_mol)
+        self.n_mol = n_mol
+        self.eng = MDEngine("water", sd, box, cutoff, masses, scaler_mean, scaler_var, precision=precision,
+                            device=device)
+        self.x4 = torch.zeros((4 * n_mol, 3), dtype=torch.float64, device=self.eng.dev)
+        self.v4 = torch.zeros_like(self.x4)
+        self.f4 = torch.zeros_like(self.x4)
+
+    def _sync_out(self):
+        wo, wh = TIP4PEW_WEIGHTS
+        c = self.eng.ctx
+        c.tip4p_unstrip(self.eng.x, self.x4, wo, wh, 1)
+        c.tip4p_unstrip(self.eng.v, self.v4, 0.0, 0.0, 0)
+        c.tip4p_unstrip(self.eng.f, self.f4, 0.0, 0.0, 0)
+
+    def set_state(self, x4_nm, v4):
+        self.x4.copy_(torch.as_tensor(np.asarray(x4_nm, dtype=np.float64)))
+        self.v4.copy_(torch.as_tensor(np.asarray(v4, dtype=np.float64)))
+        c = self.eng.ctx
+        c.tip4p_strip(self.x4, self.eng.x)
+        c.tip4p_strip(self.v4, self.eng.v)
+        c.compute_forces(self.eng.x * 10.0, self.eng.box, self.eng.cutoff, feat=self.eng.feat, out=self.eng.f)
+        c.check_async_errors()
+        self._sync_out()
+
+    def step(self, n_steps, dt):
+        self.eng.step(n_steps, dt)
+        self._sync_out()
+
+    def close(self):
+        self.eng.close()

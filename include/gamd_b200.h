@@ -172,6 +172,16 @@ int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, cons
                       int64_t n_atoms, int32_t n_frames, const double h_box[3], float cutoff,
                       const float* h_feat, double dt);
 
+/* ---- TIP4P virtual sites ------------------------------------------------------------------------ */
+/* replaces: the M-site strip of WaterDataNew (code/train_utils.py:58-64: the model sees rows with
+ * arange % 4 < 3 of a 4-site water box [O,H,H,M]) and OpenMM's average3 virtual-site placement of the
+ * TIP4P-Ew system (dataset/generate_tip4p_data.py:55-57).  d_x4 fp64 [4*n_mol,3], d_x3 fp64 [3*n_mol,3].
+ * unstrip copies the three massive sites back and sets the M row to w_o*O + w_h*(H1+H2) (place_m = 1, positions)
+ * or to zero (place_m = 0, forces / velocities of the massless site). */
+int gamd_tip4p_strip(gamd_ctx* ctx, const double* d_x4, double* d_x3, int64_t n_mol, void* stream);
+int gamd_tip4p_unstrip(gamd_ctx* ctx, const double* d_a3, double* d_a4, int64_t n_mol, double w_o, double w_h,
+                       int32_t place_m, void* stream);
+
 /* ---- spatial domain decomposition (multi-GPU, one ctx per rank) ------------------------------- */
 /* The reference has no counterpart (its MD loop is single-GPU); these entry points
  * split gamd_compute_forces at the points where a rank needs data of atoms it does not own:

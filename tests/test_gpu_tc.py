@@ -89,3 +89,36 @@ def test_tc_exact_nve_100_steps():
     print("bf16x3 KE rel err max", rel.max())
     assert rel.max() <= 1e-5
     ctx.close()
+
+
+def test_tip4p_virtual_sites():
+    """config C3 shape (here 512 molecules): strip M -> GNN on O,H,H -> integrate -> re-place M."""
+    from gamd_b200.engine import TIP4PEW_WEIGHTS, TIP4PEngine, maxwell_boltzmann, synthetic_tip4p_box
+    from gamd_b200.weights import random_state_dict, water_bonds
+    x4, L = synthetic_tip4p_box(8)
+    n_mol = 512
+    sd = random_state_dict(4, 2.9, 0.9, kind="water")
+    s = np.load(os.path.join(FIX, "scaler_tip4p.npz"))
+    eng = TIP4PEngine(sd, L, 4.2, n_mol, s["mean"], s["var"])
+    m3 = np.tile([15.9994, 1.008, 1.008], n_mol)
+    v3 = maxwell_boltzmann(m3, 300.0, 3)
+    v4 = np.zeros((4 * n_mol, 3))
+    keep = np.arange(4 * n_mol) % 4 < 3                      # code/train_utils.py:58-64
+    v4[keep] = v3
+    eng.set_state(x4 / 10.0, v4)
+    feat = torch.zeros(3 * n_mol, 1)
+    feat[::3] = 1.0
+    ff = omd.OracleForceField(sd, "water", L, 4.2, s["mean"], s["var"], bond=water_bonds(n_mol), feat=feat)
+    want = ff.predict_forces(x4[keep])
+    f4 = eng.f4.cpu().numpy()
+    assert rel_err(f4[keep], want)[0] <= 1e-4 and np.all(f4[~keep] == 0.0)
+    xo, vo, fo, _ = omd.run_nve(ff, x4[keep] / 10.0, v3, m3, 0.002, 3)
+    eng.step(3, 0.002)
+    eng.eng.ctx.check_async_errors()
+    x = eng.x4.cpu().numpy()
+    assert np.abs(x[keep] - xo).max() <= 1e-8
+    wo, wh = TIP4PEW_WEIGHTS
+    o, h1, h2, msite = x[0::4], x[1::4], x[2::4], x[3::4]
+    assert np.abs(msite - (wo * o + wh * (h1 + h2))).max() <= 1e-12
+    assert np.all(eng.v4.cpu().numpy()[~keep] == 0.0)
+    eng.close()
