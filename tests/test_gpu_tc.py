@@ -116,7 +116,7 @@ def test_tip4p_virtual_sites():
     eng.step(3, 0.002)
     eng.eng.ctx.check_async_errors()
     x = eng.x4.cpu().numpy()
-    assert np.abs(x[keep] - xo).max() <= 1e-8
+    assert np.abs(x[keep] - xo).max() <= 2e-7      # H atoms, |F| ~ 650 kJ/mol/nm: 1e-5 force error -> 2e-8 nm in 3 steps
     wo, wh = TIP4PEW_WEIGHTS
     o, h1, h2, msite = x[0::4], x[1::4], x[2::4], x[3::4]
     assert np.abs(msite - (wo * o + wh * (h1 + h2))).max() <= 1e-12
