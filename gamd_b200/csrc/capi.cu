@@ -247,6 +247,7 @@ int gamd_destroy(gamd_ctx* ctx) {
   if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
   if (ctx->d_wimg_enc) cudaFree(ctx->d_wimg_enc);
   if (ctx->d_tc_bias_enc) cudaFree(ctx->d_tc_bias_enc);
+  if (ctx->d_wimg_node) cudaFree(ctx->d_wimg_node);
   if (ctx->d_bond) cudaFree(ctx->d_bond);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
@@ -494,6 +495,32 @@ int gamd_finalize_weights(gamd_ctx* ctx) {
     GAMD_CUDA(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
     GAMD_CUDA(cudaMalloc(&ctx->d_tc_bias, tb.size() * sizeof(float)));
     GAMD_CUDA(cudaMemcpy(ctx->d_tc_bias, tb.data(), tb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // node matrices of every layer (+ the decoder's first Linear in slot 5 of every slab)
+    {
+      std::vector<uint8_t> nimg((size_t)d.conv_layer * 6 * 2 * chunk, 0);
+      const char* nn[5] = {"phi_edge", "phi.mlp_layer.1", "src_affine", "dst_affine", "phi_dst"};
+      for (int l = 0; l < d.conv_layer; l++)
+        for (int mtx = 0; mtx < 6; mtx++) {
+          const std::string key = mtx < 5 ? "graph_conv.conv." + std::to_string(l) + "." + nn[mtx] + ".weight"
+                                          : std::string("graph_decoder.mlp_layer.0.weight");
+          const std::vector<float>& w = ctx->host_w[key];
+          uint8_t* hi = nimg.data() + ((size_t)(l * 6 + mtx) * 2 + 0) * chunk;
+          uint8_t* lo = hi + chunk;
+          for (int n = 0; n < 128; n++)
+            for (int k = 0; k < 128; k++) {
+              float x = w[(size_t)n * 128 + k];
+              uint16_t h = bf16_rn(x);
+              uint16_t lw = bf16_rn(x - bf16_f(h));
+              size_t off = (size_t)(k >> 6) * 16384 + (size_t)n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + ((k & 7) << 1);
+              memcpy(hi + off, &h, 2);
+              memcpy(lo + off, &lw, 2);
+            }
+        }
+      if (ctx->d_wimg_node) cudaFree(ctx->d_wimg_node);
+      ctx->d_wimg_node = nullptr;
+      GAMD_CUDA(cudaMalloc(&ctx->d_wimg_node, nimg.size()));
+      GAMD_CUDA(cudaMemcpy(ctx->d_wimg_node, nimg.data(), nimg.size(), cudaMemcpyHostToDevice));
+    }
     // edge encoder: enc0 [128 x n_in] zero-padded to K = 64 (one K block), enc2 / enc4 [128 x 128]
     {
       std::vector<uint8_t> eimg(2 * 16384 + 4 * 32768, 0);

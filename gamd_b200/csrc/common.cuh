@@ -60,6 +60,7 @@ struct gamd_ctx {
   float* d_tc_bias = nullptr;     // [layer][4][128]
   uint8_t* d_wimg_enc = nullptr;  // edge encoder images: enc0 hi|lo (16 KB each, K=64), enc2 hi|lo, enc4 hi|lo (32 KB each)
   float* d_tc_bias_enc = nullptr; // [3][128]
+  uint8_t* d_wimg_node = nullptr; // node matrices: [layer][pedge, phi, src, dst, pdst, dec0][hi|lo][32 KB]
   int* d_bond = nullptr;          // [atoms_per_frame][GAMD_MAX_BOND] frame-local partner ids, -1 padded
   int64_t bond_atoms = 0;
 
@@ -148,6 +149,7 @@ int csr_from_sorted_coo(gamd_ctx* ctx, const int64_t* d_center, const int64_t* d
 int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cudaStream_t st);
 
 int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st);
+int node_update_tc_launch(gamd_ctx* ctx, int mode, int layer, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int atoms_per_frame,
                           const float box[3], cudaStream_t st);
 int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64_t n_atoms, int atoms_per_frame,

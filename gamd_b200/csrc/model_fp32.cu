@@ -571,10 +571,14 @@ int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64
   NodeArgs na = node_args(mw);
   na.next = mw.layer[0];
   prof_mark(ctx, "node_update", st);
-  k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
-                                                          ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd,
-                                                          ctx->pred);
-  GAMD_LAUNCH_CHECK();
+  if (tcpath) {
+    if ((rc = node_update_tc_launch(ctx, 0, 0, pos_feat, n_atoms, st))) return rc;
+  } else {
+    k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
+                                                            ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd,
+                                                            ctx->pred);
+    GAMD_LAUNCH_CHECK();
+  }
   prof_mark(ctx, "node_update", st);
   return 0;
 }
@@ -602,6 +606,12 @@ int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, c
   prof_mark(ctx, "node_update", st);
   NodeArgs na = node_args(mw);
   na.cur = mw.layer[l];
+  if (tcpath) {
+    int rc = node_update_tc_launch(ctx, l + 1 < mw.n_layers ? 1 : 2, l, pos_feat, n_atoms, st);
+    if (rc) return rc;
+    prof_mark(ctx, "node_update", st);
+    return 0;
+  }
   if (l + 1 < mw.n_layers) {
     na.next = mw.layer[l + 1];
     k_node_update<false, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,

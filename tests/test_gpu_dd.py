@@ -90,7 +90,9 @@ def test_slab_md_equals_single_domain(world):
     scale = np.abs(f_ref).max()
     err = np.abs(ret["f0"] - f_ref).max() / scale
     print(f"world {world}: halo {ret['halo']} force err {err:.2e} x err {np.abs(ret['x5'] - x_ref).max():.2e}")
-    assert err <= 2e-5                                    # summation-order differences only
+    # the edge sets are identical; only the summation order inside a receiver row differs, which the bf16x3
+    # hi/lo rounding turns into differences at the mode's own noise level (~1e-5, tolerance 1e-4)
+    assert err <= 1e-4
     assert np.abs(ret["x5"] - x_ref).max() <= 1e-7
     assert abs(ret["ke"] - ke_ref) / ke_ref <= 1e-6
     if world > 1:
