@@ -883,6 +883,7 @@ int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_byt
   else if (n == "hn") p = ctx->hn, nb = 4 * A * GAMD_NF;
   else if (n == "agg") p = ctx->agg, nb = 4 * A * GAMD_NF;
   else if (n == "pred") p = ctx->pred, nb = 4 * A * 3;
+  else if (n == "dbg") p = ctx->e_emb + (size_t)E * GAMD_NF, nb = 256 * GAMD_NF * 4;
   else {
     ctx->err = "unknown debug buffer: " + n;
     return GAMD_EINVAL;

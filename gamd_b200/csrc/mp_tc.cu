@@ -18,6 +18,7 @@
 // that straddle a 32-edge block go to the `part` side buffer and are summed (in order) by the node kernel.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace {
 using namespace tc;
@@ -46,6 +47,7 @@ struct MpTcArgs {
   const float *hn, *srcA, *dstA;
   float *agg, *part;
   int exact;
+  long long* dbg;   // development: clock64 timeline of CTA 0 (nullptr = off)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
   if (tid == 0) {
     for (int i = 0; i < RING; i++) {
       mbar_init(&sm.full[i], 1);
-      mbar_init(&sm.empty[i], 1);
+      mbar_init(&sm.empty[i], 2);   // both tile slots must have consumed a weight stage before it is replaced
     }
     for (int g = 0; g < 2; g++) {
       mbar_init(&sm.a_ready[g], 256);
@@ -258,14 +260,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
     uint64_t* const a_bar = &sm.a_ready[g];
     uint64_t* const d_bar = &sm.d_ready[g];
     uint32_t d_par = 0;
+    long long* dbg_rec = a.dbg ? a.dbg + warp * 256 : nullptr;
+    int dbg_n = 0;
+    // endpoints of my edge in the first tile; the next tile's are fetched while the current one is processed
+    int nsrc = 0, ndst = -1;
+    {
+      const int t0 = blockIdx.x * 2 + g;
+      const int e_first = t0 * TILE + r;
+      if (t0 < ntiles && e_first < E) {
+        nsrc = a.col[e_first];
+        ndst = a.edst[e_first];
+      }
+    }
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int tile = pair * 2 + g;
       if (tile >= ntiles) continue;
+      const bool dbg_on = dbg_rec && blockIdx.x == 0 && lane == 0 && dbg_n + 14 <= 256;
+      if (dbg_on) dbg_rec[dbg_n++] = clock64();
       const int e0 = tile * TILE;
       const int e = e0 + r;
       c.valid = e < E;
-      c.src = c.valid ? a.col[e] : 0;
-      const int dst = c.valid ? a.edst[e] : -1;
+      c.src = nsrc;
+      const int dst = ndst;
+      // e tile loads first: they depend on nothing but the tile index
+      const uint4* bh = reinterpret_cast<const uint4*>(a.e_blob + (size_t)tile * 65536) + (ch * 8) * 128 + r;
+      uint4 q[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) q[i] = __ldg(bh + i * 128);
+      {  // endpoints of my edge in the next tile of this slot
+        const int ntile = tile + 2 * (int)gridDim.x;
+        const int en = ntile * TILE + r;
+        nsrc = 0;
+        ndst = -1;
+        if (ntile < ntiles && en < E) {
+          nsrc = a.col[en];
+          ndst = a.edst[en];
+        }
+      }
       c.dst_row = reinterpret_cast<const float4*>(a.dstA + (size_t)(dst < 0 ? 0 : dst) * 128 + c.col0);
       issue_gather(c, 0);
       {  // pull my share of the NEXT tile's e blob into L2 while this tile is being processed
@@ -282,14 +313,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
 
       // ---- stage 0 operand: my half of the e tile (bf16 hi / lo) -> TMEM A ------------------
       {
-        const uint4* bh = reinterpret_cast<const uint4*>(a.e_blob + (size_t)tile * 65536) + (ch * 8) * 128 + r;
 #pragma unroll
         for (int part = 0; part < 2; part++) {
-          if (part == 1 && !exact) break;
-          const uint4* bp = bh + part * (32768 / 16);
-          uint4 q[8];
+          if (part == 1) {
+            if (!exact) break;
 #pragma unroll
-          for (int i = 0; i < 8; i++) q[i] = __ldg(bp + i * 128);
+            for (int i = 0; i < 8; i++) q[i] = __ldg(bh + 32768 / 16 + i * 128);
+          }
 #pragma unroll
           for (int c2 = 0; c2 < 2; c2++) {
             uint32_t h[16];
@@ -305,6 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
         tc_fence_before();
         mbar_arrive(a_bar);
       }
+      if (dbg_on) dbg_rec[dbg_n++] = clock64();
 
       // segment structure of my warp's 32 rows (receiver-sorted)
       c.same = 0;   // bit k: row (lane - 2^k) belongs to my segment
@@ -326,16 +357,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
       }
 
 #define GAMD_STAGE(S)                              \
+  if (dbg_on) dbg_rec[dbg_n++] = clock64();        \
   mbar_wait(d_bar, d_par);                         \
   d_par ^= 1;                                      \
   tc_fence_after();                                \
+  if (dbg_on) dbg_rec[dbg_n++] = clock64();        \
   if (exact) stage_epilogue<S, true>(c);           \
   else stage_epilogue<S, false>(c);                \
   if (S < 3) {                                     \
     tmem_wait_st();                                \
     tc_fence_before();                             \
     mbar_arrive(a_bar);                            \
-  }
+  }                                                \
+  if (dbg_on) dbg_rec[dbg_n++] = clock64();
       GAMD_STAGE(0)
       GAMD_STAGE(1)
       GAMD_STAGE(2)
@@ -343,76 +377,90 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
 #undef GAMD_STAGE
     }
   } else if (warp == MMA_WARP) {
-    // ===================== MMA issue (one thread) =====================
+    // ===================== MMA issue (one thread): an event loop over the two tiles in flight =====================
+    // Each tile slot walks its own sequence of (pair, stage) steps Q = 4 * pair_iteration + stage and is served as
+    // soon as its A operand is in TMEM and the weights of that stage are in shared memory, independently of the
+    // other slot.  bf16x3: weights live in two slot pairs (hi, lo) indexed by Q & 1; a pair is reloaded with stage
+    // Q + 2 once BOTH tiles have consumed stage Q (wempty counts 2), so the slots may drift apart by one stage.
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const int n_my_pairs = blockIdx.x < npairs ? (npairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+      const int totalQ = 4 * n_my_pairs;
+      int Qg[2] = {0, 0};
       uint32_t a_par[2] = {0, 0};
-      uint32_t q = 0;
-      bool first = true;
-      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        for (int s = 0; s < 4; s++) {
-          uint32_t slot_hi, slot_lo = 0;
-          if (a.exact) {
-            slot_hi = q % RING;
-            slot_lo = (q + 1) % RING;
-            mbar_wait(&sm.full[slot_hi], (q / RING) & 1);
-            mbar_wait(&sm.full[slot_lo], ((q + 1) / RING) & 1);
-          } else {
-            slot_hi = s;
-            if (first) mbar_wait(&sm.full[s], 0);
-          }
-          const uint32_t bhi = smem_u32(sm.w[slot_hi]), blo = smem_u32(sm.w[slot_lo]);
-          for (int g = 0; g < 2; g++) {
-            if (pair * 2 + g >= ntiles) continue;
-            mbar_wait(&sm.a_ready[g], a_par[g]);
-            a_par[g] ^= 1;
-            tc_fence_after();
-            const uint32_t d = tb + g * 256, ah = d + 128, al = d + 192;
-            const int passes = a.exact ? 3 : 1;
-            uint32_t accum = 0;
-            for (int p = 0; p < passes; p++) {
-              const uint32_t bb = (p == 2) ? blo : bhi;
-              const uint32_t aa = (p == 1) ? al : ah;
+      bool w_res = false;   // bf16 mode: all four hi images resident after the first load
+      uint32_t spins = 0;
+      while (Qg[0] < totalQ || Qg[1] < totalQ) {
+        bool progressed = false;
 #pragma unroll
-              for (int ks = 0; ks < 8; ks++) {
-                umma_ts(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum);
-                accum = 1;
-              }
-            }
-            umma_commit(&sm.d_ready[g]);
-          }
+        for (int g = 0; g < 2; g++) {
+          const int Q = Qg[g];
+          if (Q >= totalQ) continue;
+          const int s = Q & 3;
+          const int pair = blockIdx.x + (Q >> 2) * gridDim.x;
+          const bool tile_valid = pair * 2 + g < ntiles;
+          const int sp = Q & 1;
           if (a.exact) {
-            umma_commit(&sm.empty[slot_hi]);
-            umma_commit(&sm.empty[slot_lo]);
-            q += 2;
+            if (!mbar_try_wait(&sm.full[sp], (Q >> 1) & 1)) continue;
+          } else if (!w_res) {
+            if (!mbar_try_wait(&sm.full[0], 0)) continue;
+            w_res = true;
           }
+          if (!tile_valid) {          // absent second tile of the tail pair: release the weights on its behalf
+            if (a.exact) mbar_arrive(&sm.empty[sp]);
+            Qg[g]++;
+            progressed = true;
+            continue;
+          }
+          if (!mbar_try_wait(&sm.a_ready[g], a_par[g])) continue;
+          a_par[g] ^= 1;
+          tc_fence_after();
+          const uint32_t bhi = smem_u32(a.exact ? sm.w[2 * sp] : sm.w[s]);
+          const uint32_t blo = smem_u32(sm.w[2 * sp + 1]);
+          const uint32_t d = tb + g * 256, ah = d + 128, al = d + 192;
+          const int passes = a.exact ? 3 : 1;
+          uint32_t accum = 0;
+          for (int p = 0; p < passes; p++) {
+            const uint32_t bb = (p == 2) ? blo : bhi;
+            const uint32_t aa = (p == 1) ? al : ah;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+              umma_ts(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum);
+              accum = 1;
+            }
+          }
+          umma_commit(&sm.d_ready[g]);
+          if (a.exact) umma_commit(&sm.empty[sp]);
+          Qg[g]++;
+          progressed = true;
         }
-        first = false;
+        if (progressed) spins = 0;
+        else if (++spins > (1u << 26)) __trap();
       }
     }
     __syncwarp();
   } else {
     // ===================== weight producer (one thread) =====================
     if (lane == 0) {
-      auto load = [&](int slot, int stage, int part) {
-        mbar_arrive_expect_tx(&sm.full[slot], WCHUNK);
-        const uint8_t* src = a.w_img + ((size_t)stage * 2 + part) * WCHUNK;
-#pragma unroll
-        for (int i = 0; i < 4; i++) bulk_g2s(sm.w[slot] + i * 8192, src + i * 8192, 8192, &sm.full[slot]);
-      };
+      const int n_my_pairs = blockIdx.x < npairs ? (npairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       if (!a.exact) {
-        if (blockIdx.x < npairs)
-          for (int s = 0; s < 4; s++) load(s, s, 0);
-      } else {
-        uint32_t q = 0;
-        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x)
+        if (n_my_pairs) {
+          mbar_arrive_expect_tx(&sm.full[0], 4 * WCHUNK);
           for (int s = 0; s < 4; s++)
-            for (int part = 0; part < 2; part++) {
-              const int slot = q % RING;
-              if (q >= RING) mbar_wait(&sm.empty[slot], ((q / RING) - 1) & 1);
-              load(slot, s, part);
-              q++;
-            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+              bulk_g2s(sm.w[s] + i * 8192, a.w_img + (size_t)s * 2 * WCHUNK + i * 8192, 8192, &sm.full[0]);
+        }
+      } else {
+        const int totalQ = 4 * n_my_pairs;
+        for (int Q = 0; Q < totalQ; Q++) {
+          const int sp = Q & 1, n = Q >> 1;
+          if (n >= 1) mbar_wait(&sm.empty[sp], (n - 1) & 1);
+          mbar_arrive_expect_tx(&sm.full[sp], 2 * WCHUNK);
+          const uint8_t* src = a.w_img + (size_t)(Q & 3) * 2 * WCHUNK;     // [hi | lo] of this stage, contiguous
+#pragma unroll
+          for (int i = 0; i < 8; i++) bulk_g2s(sm.w[2 * sp] + i * 8192, src + i * 8192, 8192, &sm.full[sp]);
+        }
       }
     }
     __syncwarp();
@@ -445,6 +493,7 @@ int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st) {
   a.agg = ctx->agg;
   a.part = ctx->part;
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
+  a.dbg = (getenv("GAMD_TIMELINE") && layer == 1) ? reinterpret_cast<long long*>(ctx->e_emb + (size_t)ctx->cap_edges * 128) : nullptr;
   k_mp_edge_tc<<<ctx->sm_count, THREADS, smem, st>>>(a);
   GAMD_LAUNCH_CHECK();
   return 0;
