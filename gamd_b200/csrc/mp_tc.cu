@@ -14,8 +14,9 @@
 // CTA = 18 warps: 16 epilogue warps (thread = edge row; two 128-edge tiles in flight, 8 warps each = 4 TMEM
 // lane quadrants x 2 column halves; the two tiles ping-pong on the tensor core and share every weight
 // load), 1 MMA-issue warp, 1 weight-producer warp.  Neighbour features are gathered with coalesced cp.async into per-warp staging rows; the final
-// segmented sum is a warp-shuffle segmented scan over the receiver-sorted rows - no atomics; rows
-// that straddle a 32-edge block go to the `part` side buffer and are summed (in order) by the node kernel.
+// segmented sum walks the receiver-sorted rows in order (messages transposed through the staging tile, lane =
+// feature column) - no atomics, deterministic; rows that straddle a 32-edge block go to the `part` side buffer
+// and are summed (in order) by the node kernel.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
@@ -71,6 +72,14 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem) : "memory");
 }
@@ -85,7 +94,7 @@ struct EpiCtx {
   uint32_t bias_addr;           // shared address of bias[0][col0]
   int col0, src;
   bool valid;
-  uint32_t same;
+  uint32_t end_mask;            // bit j: row j of my warp's 32 rows is the last edge of a receiver run (in this block)
   float* out_row;
   const float4* dst_row;
   const float *srcA, *hn;
@@ -183,31 +192,51 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
         tmem_st8(c.AH + cc * 8, h);
       }
     } else {
-      // message = hn[src] * e_emb, then segmented inclusive scan down the receiver-sorted rows
+      // message = hn[src] * e_emb; parked (fp32) in my own accumulator columns until all four chunks are done
+      uint32_t pr[16];
 #pragma unroll
       for (int j4 = 0; j4 < 4; j4++) {
         const float4 hv = lds128(grow + j4 * 16);
-        x[4 * j4] = c.valid ? x[4 * j4] * hv.x : 0.f;
-        x[4 * j4 + 1] = c.valid ? x[4 * j4 + 1] * hv.y : 0.f;
-        x[4 * j4 + 2] = c.valid ? x[4 * j4 + 2] * hv.z : 0.f;
-        x[4 * j4 + 3] = c.valid ? x[4 * j4 + 3] * hv.w : 0.f;
+        pr[4 * j4] = __float_as_uint(c.valid ? x[4 * j4] * hv.x : 0.f);
+        pr[4 * j4 + 1] = __float_as_uint(c.valid ? x[4 * j4 + 1] * hv.y : 0.f);
+        pr[4 * j4 + 2] = __float_as_uint(c.valid ? x[4 * j4 + 2] * hv.z : 0.f);
+        pr[4 * j4 + 3] = __float_as_uint(c.valid ? x[4 * j4 + 3] * hv.w : 0.f);
       }
+      tmem_st16(c.Dc + cc * 16, pr);
+    }
+  }
+  if (S == 3) {
+    // segmented sum over the receiver-sorted rows, without atomics and without shuffles: the 32 x 32 block of
+    // messages is transposed through my warp's (now idle) staging buffers, lane = feature column walks down the
+    // rows in order and stores a finished receiver's 32 sums as one coalesced 128-byte row segment
+    tmem_wait_st();
+    const uint32_t T = c.gbuf[0];              // 32 rows x 36 words (both staging buffers, 4608 B)
+    const uint32_t lane = c.grow_off / GROW;
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+      uint32_t v0[16], v1[16];
+      tmem_ld16(c.Dc + p * 32, v0);
+      tmem_ld16(c.Dc + p * 32 + 16, v1);
+      tmem_wait_ld();
+      __syncwarp();
 #pragma unroll
-      for (int k = 0; k < 5; k++) {
-        const bool take = (c.same >> k) & 1u;
+      for (int j4 = 0; j4 < 4; j4++) {
+        sts128(T + lane * 144 + j4 * 16, v0[4 * j4], v0[4 * j4 + 1], v0[4 * j4 + 2], v0[4 * j4 + 3]);
+        sts128(T + lane * 144 + 64 + j4 * 16, v1[4 * j4], v1[4 * j4 + 1], v1[4 * j4 + 2], v1[4 * j4 + 3]);
+      }
+      __syncwarp();
+      float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const float u = __shfl_up_sync(0xffffffffu, x[j], 1 << k);
-          if (take) x[j] += u;
+      for (int j = 0; j < 32; j++) {
+        acc += lds32(T + j * 144 + lane * 4);
+        if ((c.end_mask >> j) & 1u) {
+          const unsigned long long ptr = __shfl_sync(0xffffffffu, (unsigned long long)c.out_row, j);
+          reinterpret_cast<float*>(ptr)[p * 32 + lane] = acc;
+          acc = 0.f;
         }
       }
-      if (c.out_row) {
-#pragma unroll
-        for (int j4 = 0; j4 < 4; j4++)
-          *reinterpret_cast<float4*>(c.out_row + cc * 16 + j4 * 4) =
-              make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
-      }
     }
+    __syncwarp();
   }
 }
 
@@ -337,16 +366,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
       }
       if (dbg_on) dbg_rec[dbg_n++] = clock64();
 
-      // segment structure of my warp's 32 rows (receiver-sorted)
-      c.same = 0;   // bit k: row (lane - 2^k) belongs to my segment
-#pragma unroll
-      for (int k = 0; k < 5; k++) {
-        const int od = __shfl_up_sync(0xffffffffu, dst, 1 << k);
-        if (lane >= (1 << k) && od == dst) c.same |= 1u << k;
-      }
+      // receiver runs inside my warp's 32 rows (receiver-sorted): where they end and where their sums go
       const int nd = __shfl_down_sync(0xffffffffu, dst, 1);
+      const bool seg_end = c.valid && (lane == 31 || nd != dst);
+      c.end_mask = __ballot_sync(0xffffffffu, seg_end);
       c.out_row = nullptr;
-      if (c.valid && (lane == 31 || nd != dst)) {
+      if (seg_end) {
         const int bstart = e0 + wq * 32;
         const int bend = min(bstart + 32, E);
         const int blk = bstart >> 5;
