@@ -340,6 +340,10 @@ def run_ours(args):
     mp_avg_s = mp_ms / max(mp_cnt, 1) * 1e-3
     flop_per_launch = 131072.0 * n_edges            # 4 x (128x128) mat-vec per edge
     achieved = flop_per_launch / mp_avg_s / 1e12 if mp_avg_s > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tpath) and world == 1:
+        traffic = json.load(open(tpath)).get(f"{args.workload}:{args.precision}:k_mp_edge_tc")
     value = atoms_all * args.steps / (ms * 1e-3)
     e2e_val = atoms_all * e2e_steps / (e2e_ms * 1e-3)
     line = {
@@ -363,7 +367,8 @@ def run_ours(args):
                      # algorithmic FLOPs: 4 x (128x128) mat-vec per edge = 131072; the bf16x3 mode
                      # issues 3x that many tensor-core FLOPs (hardware_tflops) to reach fp32-grade accuracy
                      "achieved": achieved, "peak": tensor_peak / 1.0, "unit": "TFLOP/s",
-                     "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src + " bf16 sustained",
+                     "frac": achieved / tensor_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                     "algorithmic_bytes": 516.0 * n_edges + 1028.0 * n, "peak_source": peak_src + " bf16 sustained",
                      "hardware_tflops": achieved * (3 if args.precision == "bf16x3" else 1),
                      "hbm_frac": ((516.0 * n_edges + 1028.0 * n) / mp_avg_s / 1e9 / hbm_peak) if mp_avg_s > 0 else None},
         "e2e": {"value": e2e_val, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

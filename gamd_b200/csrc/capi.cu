@@ -564,11 +564,12 @@ int gamd_check_async_errors(gamd_ctx* ctx, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int flag[4] = {0, 0, 0, 0};
   int ne = 0;
-  GAMD_CUDA(cudaMemcpyAsync(flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GAMD_CUDA(cudaMemcpyAsync(flag, ctx->err_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   GAMD_CUDA(cudaMemcpyAsync(&ne, ctx->n_edges, sizeof(int), cudaMemcpyDeviceToHost, st));
   GAMD_CUDA(cudaStreamSynchronize(st));
-  if (flag[0]) GAMD_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), st));
+  if (flag[0]) GAMD_CUDA(cudaMemsetAsync(ctx->err_flag, 0, 2 * sizeof(int), st));
   if (flag[0] & 1) {
+    if (flag[1] > 0) ne = flag[1];
     ctx->err = "edge capacity exceeded: " + std::to_string(ne) + " edges needed, " + std::to_string(ctx->cap_edges) +
                " reserved; call gamd_reserve with a larger max_edges";
     return GAMD_ECAPACITY;

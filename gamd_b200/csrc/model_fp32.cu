@@ -412,6 +412,7 @@ struct NodeArgs {
 
 template <bool FIRST, bool LAST>
 __global__ void __launch_bounds__(NT) k_node_update(NodeArgs a, int n_atoms, int agg_tile,
+                                                    const int* __restrict__ n_edges_dev,
                                                     const int* __restrict__ row_ptr,
                                                     const float4* __restrict__ pos_feat,
                                                     const float* __restrict__ agg, const float* __restrict__ part,
@@ -448,6 +449,7 @@ __global__ void __launch_bounds__(NT) k_node_update(NodeArgs a, int n_atoms, int
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n_atoms) {
           int rs = row_ptr[i], re = row_ptr[i + 1];
+          if (*n_edges_dev == 0) re = rs;   // empty / overflowed edge list (k_nbr_guard)
           if (re > rs) {
             int t0 = rs / agg_tile, t1 = (re - 1) / agg_tile;
             if (t0 == t1) {
@@ -574,7 +576,7 @@ int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64
   if (tcpath) {
     if ((rc = node_update_tc_launch(ctx, 0, 0, pos_feat, n_atoms, st))) return rc;
   } else {
-    k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
+    k_node_update<true, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->n_edges, ctx->row_ptr, pos_feat, ctx->agg,
                                                             ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd,
                                                             ctx->pred);
     GAMD_LAUNCH_CHECK();
@@ -614,11 +616,11 @@ int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, c
   }
   if (l + 1 < mw.n_layers) {
     na.next = mw.layer[l + 1];
-    k_node_update<false, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
+    k_node_update<false, false><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->n_edges, ctx->row_ptr, pos_feat, ctx->agg,
                                                              ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd,
                                                              ctx->pred);
   } else {
-    k_node_update<false, true><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->row_ptr, pos_feat, ctx->agg,
+    k_node_update<false, true><<<grid_node, NT, smem, st>>>(na, (int)n_atoms, agg_tile, ctx->n_edges, ctx->row_ptr, pos_feat, ctx->agg,
                                                             ctx->part, ctx->h, ctx->hn, ctx->srcA, ctx->dstA, ctx->pd,
                                                             ctx->pred);
   }

@@ -478,6 +478,17 @@ int nbr_bin_f64(gamd_ctx* ctx, const double* d_x, double scale, const double* bo
   return 0;
 }
 
+// edge capacity exceeded: flag it and publish an EMPTY edge list so that no downstream kernel can index past the
+// reserved buffers (the error surfaces at the next gamd_check_async_errors as GAMD_ECAPACITY with the needed size)
+__global__ void k_nbr_guard(const int* __restrict__ row_ptr, int n, int cap, int* __restrict__ n_edges,
+                            int* __restrict__ err_flag) {
+  if (row_ptr[n] > cap) {
+    atomicOr(err_flag, 1);
+    err_flag[1] = row_ptr[n];
+    *n_edges = 0;
+  }
+}
+
 int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, cudaStream_t st) {
   int n = p.n_atoms;
   int64_t ncells = (int64_t)p.cells_per_frame * p.n_frames;
@@ -505,6 +516,8 @@ int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, c
   GAMD_LAUNCH_CHECK();
   rc = scan_with_total(ctx, ctx->deg, ctx->row_ptr, n, ctx->n_edges, st);
   if (rc) return rc;
+  k_nbr_guard<<<1, 1, 0, st>>>(ctx->row_ptr, n, cap, ctx->n_edges, ctx->err_flag);
+  GAMD_LAUNCH_CHECK();
   if (general)
     k_sweep<true, true><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg,
                                                 ctx->row_ptr, ctx->col_idx, ctx->edge_dst, cap, ctx->err_flag);

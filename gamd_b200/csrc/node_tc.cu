@@ -467,11 +467,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
 
 // rows whose edge run straddles 32-edge blocks: agg = tail part of the first block + head parts of the others
 __global__ void k_agg_fixup(const int* __restrict__ row_ptr, const float* __restrict__ part, float* __restrict__ agg,
-                            int n_atoms) {
+                            int n_atoms, const int* __restrict__ n_edges) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n_atoms) return;
-  const int rs = row_ptr[i], re = row_ptr[i + 1];
+  int rs = row_ptr[i], re = row_ptr[i + 1];
+  if (*n_edges == 0) re = rs;      // empty / overflowed edge list (see k_nbr_guard): no receiver has edges
   float4* dst = reinterpret_cast<float4*>(agg + (size_t)i * 128) + lane;
   if (re <= rs) {
     *dst = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -499,7 +500,7 @@ int node_update_tc_launch(gamd_ctx* ctx, int mode, int layer, const float4* pos_
   }
   const ModelW& mw = ctx->mw;
   if (mode != MODE_FIRST) {
-    k_agg_fixup<<<ceil_div(n_atoms * 32, 256), 256, 0, st>>>(ctx->row_ptr, ctx->part, ctx->agg, (int)n_atoms);
+    k_agg_fixup<<<ceil_div(n_atoms * 32, 256), 256, 0, st>>>(ctx->row_ptr, ctx->part, ctx->agg, (int)n_atoms, ctx->n_edges);
     GAMD_LAUNCH_CHECK();
   }
   NodeTcArgs a{};

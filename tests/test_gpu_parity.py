@@ -305,3 +305,18 @@ def test_md_step_host_matches_device_path(lj_ctx):
     ctx.md_run(x, v, f, mt, 27.27, 7.5, 0.002, 1)
     assert np.array_equal(xh, x.cpu().numpy()) and np.array_equal(vh, v.cpu().numpy())
     assert np.array_equal(fh, f.cpu().numpy())
+
+
+@pytest.mark.parametrize("prec", [_capi.PREC_FP32, _capi.PREC_BF16X3])
+def test_force_path_survives_edge_overflow(prec):
+    """capacity exceeded inside the fused force path: no out-of-bounds work, GAMD_ECAPACITY with the needed size,
+    and the call succeeds after gamd_reserve (the analogue of graph_utils.py:40-42)."""
+    ctx, sd = make_ctx("lj", 0, 5.2, 1.5, max_atoms=512, max_edges=2000, precision=prec)
+    pos = np.load(os.path.join(FIX, "lj_init_pos.npy")).astype(np.float64)
+    with pytest.raises(_capi.GamdError) as ei:
+        ctx.compute_forces_host(pos, 27.27, 7.5)
+    assert ei.value.code == _capi.ECAPACITY and "6114" in str(ei.value)
+    ctx.reserve(512, 8192)
+    f = ctx.compute_forces_host(pos, 27.27, 7.5)
+    assert np.isfinite(f).all()
+    ctx.close()
