@@ -122,6 +122,31 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(hx, t, hx);
 }
 
+// x -> silu(x) for two elements, split into bf16 hi / lo pairs; packed fp32x2 arithmetic halves the FMA-pipe
+// instruction count of the (issue-bound) activation stages
+__device__ __forceinline__ void silu_split_pair(f32x2 X, uint32_t& hi, uint32_t& lo) {
+  const f32x2 T = mul2(X, pk2(-1.4426950408889634f, -1.4426950408889634f));
+  float t0, t1;
+  unpk2(T, t0, t1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  const f32x2 U = add2(pk2(e0, e1), pk2(1.f, 1.f));
+  float u0, u1;
+  unpk2(U, u0, u1);
+  float r0, r1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(u0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(u1));
+  const f32x2 Y = mul2(X, pk2(r0, r1));
+  float y0, y1;
+  unpk2(Y, y0, y1);
+  hi = pack_bf16(y0, y1);
+  const f32x2 R = fma2(pk2u(hi << 16, hi & 0xffff0000u), pk2(-1.f, -1.f), Y);
+  float q0, q1;
+  unpk2(R, q0, q1);
+  lo = pack_bf16(q0, q1);
+}
+
 // epilogue of GEMM stage S for my 64 columns (4 chunks of 16)
 template <int S, bool EXACT>
 __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
@@ -159,6 +184,26 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
           for (int i = 0; i < 4; i++) dn[i] = __ldg(c.dst_row + (cc + 1) * 4 + i);
         }
       }
+    }
+    if (S < 3 && EXACT) {
+      // packed path: bias (+ per-edge terms) + SiLU + bf16 hi/lo split on fp32x2 pairs
+      uint32_t h[8], l[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; j4++) {
+        const float4 b = lds128(c.bias_addr + (S * 128 + cc * 16 + j4 * 4) * 4);
+        f32x2 X0 = add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y));
+        f32x2 X1 = add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w));
+        if (S == 1) {
+          const float4 sv = lds128(grow + j4 * 16);
+          X0 = add2(X0, add2(pk2(sv.x, sv.y), pk2(dc[j4].x, dc[j4].y)));
+          X1 = add2(X1, add2(pk2(sv.z, sv.w), pk2(dc[j4].z, dc[j4].w)));
+        }
+        silu_split_pair(X0, h[2 * j4], l[2 * j4]);
+        silu_split_pair(X1, h[2 * j4 + 1], l[2 * j4 + 1]);
+      }
+      tmem_st8(c.AH + cc * 8, h);
+      tmem_st8(c.AL + cc * 8, l);
+      continue;
     }
     float x[16];
 #pragma unroll
