@@ -272,12 +272,18 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
       __syncwarp();
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        acc += lds32(T + j * 144 + lane * 4);
-        if ((c.end_mask >> j) & 1u) {
-          const unsigned long long ptr = __shfl_sync(0xffffffffu, (unsigned long long)c.out_row, j);
-          reinterpret_cast<float*>(ptr)[p * 32 + lane] = acc;
-          acc = 0.f;
+      for (int jb = 0; jb < 32; jb += 16) {
+        float t[16];   // loads batched ahead of the (serial) add chain
+#pragma unroll
+        for (int j = 0; j < 16; j++) t[j] = lds32(T + (jb + j) * 144 + lane * 4);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          acc += t[j];
+          if ((c.end_mask >> (jb + j)) & 1u) {
+            const unsigned long long ptr = __shfl_sync(0xffffffffu, (unsigned long long)c.out_row, jb + j);
+            reinterpret_cast<float*>(ptr)[p * 32 + lane] = acc;
+            acc = 0.f;
+          }
         }
       }
     }
@@ -448,6 +454,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
     }
   } else if (warp == MMA_WARP) {
     // ===================== MMA issue (one thread): an event loop over the two tiles in flight =====================
+    // (A single thread issues a tcgen05.mma only every ~120 cycles - tc_ubench.cu - so a 24-MMA stage costs ~2.9k
+    // cycles of issue.  Variants with one issuer per tile slot, two issuers per stage, or K steps issued as the
+    // previous epilogue publishes 16-column chunks were all measured SLOWER: they let the two tiles fall into
+    // lockstep on the MUFU pipe; two issuers per accumulator also lose run-to-run determinism.)
     // Each tile slot walks its own sequence of (pair, stage) steps Q = 4 * pair_iteration + stage and is served as
     // soon as its A operand is in TMEM and the weights of that stage are in shared memory, independently of the
     // other slot.  bf16x3: weights live in two slot pairs (hi, lo) indexed by Q & 1; a pair is reloaded with stage
@@ -471,9 +481,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
           const bool tile_valid = pair * 2 + g < ntiles;
           const int sp = Q & 1;
           if (a.exact) {
-            if (!mbar_try_wait(&sm.full[sp], (Q >> 1) & 1)) continue;
+            if (!mbar_test_wait(&sm.full[sp], (Q >> 1) & 1)) continue;
           } else if (!w_res) {
-            if (!mbar_try_wait(&sm.full[0], 0)) continue;
+            if (!mbar_test_wait(&sm.full[0], 0)) continue;
             w_res = true;
           }
           if (!tile_valid) {          // absent second tile of the tail pair: release the weights on its behalf
@@ -482,7 +492,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
             progressed = true;
             continue;
           }
-          if (!mbar_try_wait(&sm.a_ready[g], a_par[g])) continue;
+          if (!mbar_test_wait(&sm.a_ready[g], a_par[g])) continue;
           a_par[g] ^= 1;
           tc_fence_after();
           const uint32_t bhi = smem_u32(a.exact ? sm.w[2 * sp] : sm.w[s]);
