@@ -293,7 +293,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_encode_tc(EncTcArgs a) {
       }
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) {
+    // the whole warp runs the issue loop on warp-uniform values; only the MMAs / commits are predicated on one
+    // elected lane (tc_common.cuh: issuing from inside `if (lane == 0)` halves the MMA issue rate)
+    {
+      const uint32_t leader = elect_leader();
       const uint32_t idesc = umma_idesc_bf16(128, 128);
       uint32_t a_par[2] = {0, 0};
       bool first = true;
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_encode_tc(EncTcArgs a) {
             if (pair * 2 + g >= ntiles) continue;
             mbar_wait(&sm.a_ready[g], a_par[g]);
             a_par[g] ^= 1;
+            __syncwarp();
             tc_fence_after();
             const uint32_t d = tb + g * 256, ah = d + 128, al = d + 192;
             const int passes = exact ? 3 : 1;
@@ -319,11 +323,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_encode_tc(EncTcArgs a) {
               const uint32_t bb = wbase + off + (p == 2 ? part : 0);
               const uint32_t aa = (p == 1) ? al : ah;
               for (int ks = 0; ks < nks; ks++) {
-                umma_ts(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum);
+                umma_ts_elect(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum, leader);
                 accum = 1;
               }
             }
-            umma_commit(&sm.d_ready[g]);
+            if (leader) umma_commit(&sm.d_ready[g]);
           }
         }
       }

@@ -462,7 +462,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
     // soon as its A operand is in TMEM and the weights of that stage are in shared memory, independently of the
     // other slot.  bf16x3: weights live in two slot pairs (hi, lo) indexed by Q & 1; a pair is reloaded with stage
     // Q + 2 once BOTH tiles have consumed stage Q (wempty counts 2), so the slots may drift apart by one stage.
-    if (lane == 0) {
+    // The whole warp runs the loop on warp-uniform values; only the MMAs, commits and arrives are predicated on one
+    // elected lane (see tc_common.cuh: issuing from inside `if (lane == 0)` halves the MMA issue rate).
+    {
+      const uint32_t leader = elect_leader();
       const uint32_t idesc = umma_idesc_bf16(128, 128);
       const int n_my_pairs = blockIdx.x < npairs ? (npairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       const int totalQ = 4 * n_my_pairs;
@@ -481,18 +484,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
           const bool tile_valid = pair * 2 + g < ntiles;
           const int sp = Q & 1;
           if (a.exact) {
-            if (!mbar_test_wait(&sm.full[sp], (Q >> 1) & 1)) continue;
+            if (!__all_sync(0xffffffffu, mbar_test_wait(&sm.full[sp], (Q >> 1) & 1))) continue;
           } else if (!w_res) {
-            if (!mbar_test_wait(&sm.full[0], 0)) continue;
+            if (!__all_sync(0xffffffffu, mbar_test_wait(&sm.full[0], 0))) continue;
             w_res = true;
           }
           if (!tile_valid) {          // absent second tile of the tail pair: release the weights on its behalf
-            if (a.exact) mbar_arrive(&sm.empty[sp]);
+            if (a.exact && leader) mbar_arrive(&sm.empty[sp]);
             Qg[g]++;
             progressed = true;
             continue;
           }
-          if (!mbar_test_wait(&sm.a_ready[g], a_par[g])) continue;
+          if (!__all_sync(0xffffffffu, mbar_test_wait(&sm.a_ready[g], a_par[g]))) continue;
           a_par[g] ^= 1;
           tc_fence_after();
           const uint32_t bhi = smem_u32(a.exact ? sm.w[2 * sp] : sm.w[s]);
@@ -505,12 +508,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
             const uint32_t aa = (p == 1) ? al : ah;
 #pragma unroll
             for (int ks = 0; ks < 8; ks++) {
-              umma_ts(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum);
+              umma_ts_elect(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum,
+                            leader);
               accum = 1;
             }
           }
-          umma_commit(&sm.d_ready[g]);
-          if (a.exact) umma_commit(&sm.empty[sp]);
+          if (leader) {
+            umma_commit(&sm.d_ready[g]);
+            if (a.exact) umma_commit(&sm.empty[sp]);
+          }
+          __syncwarp();
           Qg[g]++;
           progressed = true;
         }

@@ -407,7 +407,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
       }
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) {
+    // the whole warp runs the issue loop on warp-uniform values; only the MMAs / commits are predicated on one
+    // elected lane (tc_common.cuh: issuing from inside `if (lane == 0)` halves the MMA issue rate)
+    {
+      const uint32_t leader = elect_leader();
       const uint32_t idesc = umma_idesc_bf16(128, 128);
       uint32_t a_par[2] = {0, 0};
       uint32_t q = 0;
@@ -421,6 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
             if (pair * 2 + g >= ntiles) continue;
             mbar_wait(&sm.a_ready[g], a_par[g]);
             a_par[g] ^= 1;
+            __syncwarp();
             tc_fence_after();
             const uint32_t d = tb + g * 256, ah = d + 128, al = d + 192;
             const int passes = exact ? 3 : 1;
@@ -430,14 +434,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
               const uint32_t aa = (p == 1) ? al : ah;
 #pragma unroll
               for (int ks = 0; ks < 8; ks++) {
-                umma_ts(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum);
+                umma_ts_elect(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum, leader);
                 accum = 1;
               }
             }
-            umma_commit(&sm.d_ready[g]);
+            if (leader) umma_commit(&sm.d_ready[g]);
           }
-          umma_commit(&sm.empty[slot_hi]);
-          if (exact) umma_commit(&sm.empty[slot_lo]);
+          if (leader) umma_commit(&sm.empty[slot_hi]);
+          if (exact && leader) umma_commit(&sm.empty[slot_lo]);
           q += exact ? 2 : 1;
         }
       }

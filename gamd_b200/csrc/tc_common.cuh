@@ -136,6 +136,25 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// ---- warp-uniform MMA issue --------------------------------------------------------------------
+// Issuing tcgen05.mma from inside `if (lane == 0)` makes the compiler re-elect a lane and move every operand to the
+// uniform register file for EACH instruction (VOTEU / ELECT / R2UR.BROADCAST): measured 119-133 cycles per MMA from
+// one thread, twice the 64 cycles a 128x128x16 bf16 MMA occupies the tensor pipe (tc_ubench.cu).  When the whole
+// warp runs the issue loop on warp-uniform values and only the MMA itself is predicated on one elected lane, the
+// MMAs go out back to back: measured 67.6 cycles per MMA.
+__device__ __forceinline__ uint32_t elect_leader() {   // 1 in exactly one lane of the (converged) warp
+  uint32_t leader;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+  return leader;
+}
+__device__ __forceinline__ void umma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accum, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum), "r"(leader)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -33,7 +33,17 @@ struct UArgs {
   long long* out; // [9][2] start / end clocks
 };
 
-template <bool CONST_TB>
+// warp-uniform issue: every lane executes the instruction stream, one elected lane's MMA takes effect
+__device__ __forceinline__ void umma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accum, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum), "r"(leader)
+      : "memory");
+}
+
+template <bool CONST_TB, int STYLE>
 __global__ void __launch_bounds__(320, 1) k_ubench(UArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
   USmem& sm = *reinterpret_cast<USmem*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -90,6 +100,26 @@ __global__ void __launch_bounds__(320, 1) k_ubench(UArgs a) {
       if (f == 123.f || accum == 0xdeadbeef) a.out[30] = 1;
     }
     t1 = clock64();
+  } else if (STYLE == 1 && warp == 8) {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+    const uint32_t idesc = umma_idesc_bf16(128, a.n);
+    t0 = clock64();
+    const uint64_t bd0 = umma_desc_sw128(smem_u32(sm.b[0]));
+    const uint32_t d0 = tb + 256;
+    for (int i = 0; i < a.n_mma; i += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint64_t koff = (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4);
+        umma_ts_elect(d0, tb + 128 + k * 8, bd0 + koff, idesc, (i > 0 || k > 0) ? 1u : 0u, leader);
+      }
+    }
+    if (leader) {
+      umma_commit(&sm.bar2[0]);
+      mbar_wait(&sm.bar2[0], 0);
+    }
+    __syncwarp();
+    t1 = clock64();
   } else if ((warp == 8 || (warp == 9 && a.two_issuers)) && lane == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, a.n);
     t0 = clock64();
@@ -127,9 +157,11 @@ int main() {
   long long* d_out;
   cudaMalloc(&d_out, 64 * sizeof(long long));
   const size_t smem = sizeof(USmem) + 1024;
-  cudaFuncSetAttribute(k_ubench<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(k_ubench<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  struct Case { const char* name; int n_mma, ts, ld_warps, n_ld, n_st, n_mufu, n = 128, dalt = 1, const_tb = 0, two = 0; };
+  cudaFuncSetAttribute(k_ubench<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_ubench<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_ubench<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_ubench<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  struct Case { const char* name; int n_mma, ts, ld_warps, n_ld, n_st, n_mufu, n = 128, dalt = 1, const_tb = 0, two = 0, style = 0; };
   const Case cases[] = {
       {"mma TS alone (96)", 96, 1, 0, 0, 0, 0},
       {"mma SS alone (96)", 96, 0, 0, 0, 0, 0},
@@ -159,14 +191,19 @@ int main() {
       {"mma TS N=128, two issuer warps (96 each)", 96, 1, 0, 0, 0, 0, 128, 1, 0, 1},
       {"mma TS N=128 const, two issuer warps (96 each)", 96, 1, 0, 0, 0, 0, 128, 1, 1, 1},
       {"mma TS N=64, two issuer warps (96 each)", 96, 1, 0, 0, 0, 0, 64, 1, 0, 1},
+      {"mma TS N=128 warp-uniform elect issue", 96, 1, 0, 0, 0, 0, 128, 1, 0, 0, 1},
+      {"mma TS N=128 warp-uniform elect issue, const", 96, 1, 0, 0, 0, 0, 128, 1, 1, 0, 1},
+      {"mma TS N=64 warp-uniform elect issue, const", 96, 1, 0, 0, 0, 0, 64, 1, 1, 0, 1},
   };
   for (const Case& c : cases) {
     UArgs a{c.n_mma, c.ts, c.n, c.dalt, c.two, c.const_tb, c.ld_warps, c.n_ld, c.n_st, c.n_mufu, d_out};
     long long h[64];
     for (int rep = 0; rep < 2; rep++) {   // second run is the warm one
       cudaMemset(d_out, 0, 64 * sizeof(long long));
-      if (c.const_tb) k_ubench<true><<<1, 320, smem>>>(a);
-      else k_ubench<false><<<1, 320, smem>>>(a);
+      if (c.style == 1 && c.const_tb) k_ubench<true, 1><<<1, 320, smem>>>(a);
+      else if (c.style == 1) k_ubench<false, 1><<<1, 320, smem>>>(a);
+      else if (c.const_tb) k_ubench<true, 0><<<1, 320, smem>>>(a);
+      else k_ubench<false, 0><<<1, 320, smem>>>(a);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
         printf("%s: CUDA error %s\n", c.name, cudaGetErrorString(e));
