@@ -33,16 +33,6 @@ struct UArgs {
   long long* out; // [9][2] start / end clocks
 };
 
-// warp-uniform issue: every lane executes the instruction stream, one elected lane's MMA takes effect
-__device__ __forceinline__ void umma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                              uint32_t accum, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum), "r"(leader)
-      : "memory");
-}
-
 template <bool CONST_TB, int STYLE>
 __global__ void __launch_bounds__(320, 1) k_ubench(UArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
@@ -75,11 +65,15 @@ __global__ void __launch_bounds__(320, 1) k_ubench(UArgs a) {
     t0 = clock64();
     if (warp < a.ld_warps) {
       uint32_t accum = 0;
-      for (int i = 0; i < a.n_ld; i++) {
-        tmem_ld16(base + (i & 3) * 16, v);
+      for (int i = 0; i < a.n_ld; i += 4) {   // four loads in flight per wait (throughput, not latency)
+        uint32_t w0[16], w1[16], w2[16];
+        tmem_ld16(base, v);
+        tmem_ld16(base + 16, w0);
+        tmem_ld16(base + 32, w1);
+        tmem_ld16(base + 48, w2);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; j++) accum += v[j];
+        for (int j = 0; j < 16; j++) accum += v[j] + w0[j] + w1[j] + w2[j];
       }
       for (int i = 0; i < a.n_st; i++) {
 #pragma unroll
@@ -88,21 +82,25 @@ __global__ void __launch_bounds__(320, 1) k_ubench(UArgs a) {
       }
       if (a.n_st) tmem_wait_st();
       float f = __uint_as_float((accum & 0xffff) | 0x3f800000u);
-      for (int i = 0; i < a.n_mufu; i++) {
+      float fs[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) fs[j] = f + j;
+      for (int i = 0; i < a.n_mufu; i++) {   // 16 independent ex2 + rcp chains
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           float e, r;
-          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f));
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fs[j]));
           asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-          f = f * r;
+          fs[j] = fs[j] * r;
         }
       }
+#pragma unroll
+      for (int j = 0; j < 16; j++) f += fs[j];
       if (f == 123.f || accum == 0xdeadbeef) a.out[30] = 1;
     }
     t1 = clock64();
   } else if (STYLE == 1 && warp == 8) {
-    uint32_t leader;
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+    const uint32_t leader = elect_leader();
     const uint32_t idesc = umma_idesc_bf16(128, a.n);
     t0 = clock64();
     const uint64_t bd0 = umma_desc_sw128(smem_u32(sm.b[0]));
@@ -192,6 +190,15 @@ int main() {
       {"mma TS N=128 const, two issuer warps (96 each)", 96, 1, 0, 0, 0, 0, 128, 1, 1, 1},
       {"mma TS N=64, two issuer warps (96 each)", 96, 1, 0, 0, 0, 0, 64, 1, 0, 1},
       {"mma TS N=128 warp-uniform elect issue", 96, 1, 0, 0, 0, 0, 128, 1, 0, 0, 1},
+      {"FAST mma (192) alone", 192, 1, 0, 0, 0, 0, 128, 1, 0, 0, 1},
+      {"FAST mma (192) + ld 8 warps x 128", 192, 1, 8, 128, 0, 0, 128, 1, 0, 0, 1},
+      {"FAST mma (192) + st 8 warps x 128", 192, 1, 8, 0, 128, 0, 128, 1, 0, 0, 1},
+      {"FAST mma (192) + mufu 8 warps x 32", 192, 1, 8, 0, 0, 32, 128, 1, 0, 0, 1},
+      {"FAST mma (192) + ld+st+mufu 8 warps 64/64/16", 192, 1, 8, 64, 64, 16, 128, 1, 0, 0, 1},
+      {"ld 8 warps x 128 alone", 0, 1, 8, 128, 0, 0, 128, 1, 0, 0, 1},
+      {"st 8 warps x 128 alone", 0, 1, 8, 0, 128, 0, 128, 1, 0, 0, 1},
+      {"mufu 8 warps x 32 alone", 0, 1, 8, 0, 0, 32, 128, 1, 0, 0, 1},
+      {"ld+st+mufu 8 warps 64/64/16 alone", 0, 1, 8, 64, 64, 16, 128, 1, 0, 0, 1},
       {"mma TS N=128 warp-uniform elect issue, const", 96, 1, 0, 0, 0, 0, 128, 1, 1, 0, 1},
       {"mma TS N=64 warp-uniform elect issue, const", 96, 1, 0, 0, 0, 0, 64, 1, 1, 0, 1},
   };

@@ -1,9 +1,10 @@
 """NVE energy-drift parity (north_star: "energy drift over a 10k-step NVE run must match the reference").
 
 LJ-258, random-init weights, dt = 2 fs: the GPU engine (bf16x3) runs --steps steps; the CPU oracle (the port of
-the reference path) runs --oracle-steps of them.  Compares total and COM-removed kinetic energy on the common
+the reference path) runs --oracle-steps of them (read from the committed 10k-step trace
+tests/golden/nve_lj258_oracle_ke.npy when present).  Compares total and COM-removed kinetic energy on the common
 window and the fitted drift slopes; writes profiles/nve_drift_r01.json.  Run on the GPU box:
-    python profiles/nve_drift.py --steps 10000 --oracle-steps 2000
+    python profiles/nve_drift.py --steps 10000 --oracle-steps 10000
 """
 import argparse
 import json
@@ -23,7 +24,7 @@ from oracle import md as omd  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10000)
-ap.add_argument("--oracle-steps", type=int, default=2000)
+ap.add_argument("--oracle-steps", type=int, default=10000)
 ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "nve_drift_r01.json"))
 a = ap.parse_args()
 fix = os.path.join(ROOT, "tests", "golden", "fixtures")
@@ -45,11 +46,17 @@ for name, prec in (("bf16x3", _capi.PREC_BF16X3), ("fp32", _capi.PREC_FP32), ("b
     eng.ctx.check_async_errors()
     res[name] = dict(ke=ke.cpu().numpy(), ms_per_step=dt_wall / a.steps * 1e3)
     eng.close()
-t0 = time.perf_counter()
-ff = omd.OracleForceField(sd, "lj", 27.27, 7.5, s["mean"], s["var"])
-_, _, _, trace = omd.run_nve(ff, pos / 10.0, v0, m, 0.002, a.oracle_steps)
-t_or = time.perf_counter() - t0
-ko = trace[:, 1]
+golden = os.path.join(ROOT, "tests", "golden", "nve_lj258_oracle_ke.npy")
+if os.path.exists(golden) and len(np.load(golden)) >= a.oracle_steps:
+    # committed 10k-step oracle trace (tests/golden/make_nve_golden.py): same system, seed and step
+    ko = np.load(golden)[:a.oracle_steps]
+    t_or = float("nan")
+else:
+    t0 = time.perf_counter()
+    ff = omd.OracleForceField(sd, "lj", 27.27, 7.5, s["mean"], s["var"])
+    _, _, _, trace = omd.run_nve(ff, pos / 10.0, v0, m, 0.002, a.oracle_steps)
+    t_or = time.perf_counter() - t0
+    ko = trace[:, 1]
 t = np.arange(1, a.steps + 1) * 0.002
 out = {"system": "LJ-258, dt 2 fs, random-init MDNet (PCG64 seed 0, length stats 5.2/1.5), scaler_lj", "steps": a.steps,
        "oracle_steps": a.oracle_steps, "oracle_s_per_step": t_or / a.oracle_steps}
@@ -60,6 +67,8 @@ for name, r in res.items():
         "ms_per_step": r["ms_per_step"],
         "ke_rel_err_vs_oracle_max": float(np.abs(k[:n] - ko).max() / ko.max()),
         "ke_rel_err_vs_oracle_at_end_of_window": float(abs(k[n - 1] - ko[-1]) / ko[-1]),
+        "ke_rel_err_vs_oracle_at_steps": {str(c): float(abs(k[c - 1] - ko[c - 1]) / ko[c - 1])
+                                          for c in (100, 1000, 2000, 5000, 10000) if c <= n},
         "drift_slope_kJ_per_mol_per_ps_first_window": float(np.polyfit(t[:n], k[:n], 1)[0]),
         "drift_slope_full_run": float(np.polyfit(t, k, 1)[0]),
         "ke_first_last": [float(k[0]), float(k[-1])],

@@ -108,3 +108,18 @@ def test_wrap_matches_torch_remainder_and_branchy_form():
         # branchy add/sub is bit-identical to fmod-based mod for |t| < 2L except where the
         # double add rounds differently; the CUDA kernel uses fmodf, this documents the claim
         assert (br.astype(np.float32) != onb.wrap_f32(t, L)).mean() < 1e-3
+
+
+def test_nve_trace_fixture_is_the_oracle(golden_dir, fixtures_dir):
+    """the committed 10k-step kinetic-energy trace (tests/golden/make_nve_golden.py) is what the oracle produces:
+    its first 40 steps are regenerated here."""
+    from gamd_b200.engine import maxwell_boltzmann
+    from oracle import md as omd
+    ko = np.load(os.path.join(golden_dir, "nve_lj258_oracle_ke.npy"))
+    assert ko.shape == (10000,)
+    pos = np.load(os.path.join(fixtures_dir, "lj_init_pos.npy")).astype(np.float64)
+    sc = np.load(os.path.join(fixtures_dir, "scaler_lj.npz"))
+    m = np.full(258, 39.9)
+    ff = omd.OracleForceField(random_state_dict(0, 5.2, 1.5, kind="lj"), "lj", 27.27, 7.5, sc["mean"], sc["var"])
+    _, _, _, trace = omd.run_nve(ff, pos / 10.0, maxwell_boltzmann(m, 100.0, 1234), m, 0.002, 40)
+    np.testing.assert_allclose(trace[:, 1], ko[:40], rtol=1e-9)
