@@ -5,7 +5,8 @@ Two ways the path shards:
 * **replicas / frames** - independent systems; ``shard_replicas`` splits them contiguously over ranks, there
   is no data-path collective (only scalar observables are reduced when reported).
 * **spatial domain decomposition** (``SlabDomainMD``) - slabs along x with periodic neighbours.  Per step:
-  owned atoms that drifted out of the slab migrate; positions of owned atoms within the cutoff of a face are
+  owned atoms that drifted out of the slab migrate (every step, or every ``migrate_every`` steps with the halo
+  widened by ``SlabPlan.margin`` so that a stray atom's neighbourhood stays complete); positions of owned atoms within the cutoff of a face are
   sent to that neighbour (halo); each rank runs the neighbor search over owned + halo atoms with the GLOBAL
   periodic box (halo atoms are neighbours only); after each message-passing layer but the last, the rows
   ``[LN(h) | src_affine(LN(h))]`` of the halo atoms are refreshed from their owners (layer 0 needs none: its
@@ -32,12 +33,14 @@ def shard_replicas(n_replicas, world, rank):
 class SlabPlan:
     """Ownership and halo geometry of a 1-D slab decomposition along x (Angstrom)."""
 
-    def __init__(self, box, cutoff, world, rank):
+    def __init__(self, box, cutoff, world, rank, margin=0.0):
         self.box = np.broadcast_to(np.asarray(box, dtype=np.float64), (3,)).copy()
         self.world, self.rank = world, rank
         self.width = self.box[0] / world
-        # every atom that can pass the fp32 predicate dr2 < rc^2 of an owned atom lies within this distance
-        self.halo = float(cutoff) * 1.002 + 1e-3
+        # every atom that can pass the fp32 predicate dr2 < rc^2 of an owned atom lies within this distance;
+        # `margin` (Angstrom) is how far an owned atom may stray out of its slab between two migrations
+        self.margin = float(margin)
+        self.halo = float(cutoff) * 1.002 + 1e-3 + self.margin
         if world > 1 and self.width < self.halo:
             raise ValueError(f"slab width {self.width:.2f} A is smaller than the cutoff: use fewer ranks")
         self.lo, self.hi = rank * self.width, (rank + 1) * self.width
@@ -54,6 +57,18 @@ class SlabPlan:
     def halo_masks(self, xw):
         """(to_left, to_right): owned atoms whose position must be known to the left / right neighbour."""
         return xw - self.lo < self.halo, self.hi - xw < self.halo
+
+    def centered(self, x_col):
+        """signed x offset (Angstrom) from the centre of my slab, periodic, in [-Lx/2, Lx/2): also meaningful for
+        an atom that has strayed out of the slab (|offset| > width / 2), across the box boundary or not."""
+        L = float(self.box[0])
+        c = 0.5 * (self.lo + self.hi)
+        return torch.remainder(x_col - (c - 0.5 * L), L) - 0.5 * L
+
+    def halo_masks_centered(self, dx):
+        """same as ``halo_masks`` on centred offsets; strays (beyond a face) are always sent to that side."""
+        half = 0.5 * self.width
+        return dx + half < self.halo, half - dx < self.halo
 
 
 def _exchange(send_left, send_right, plan, n_from_left, n_from_right):
@@ -89,18 +104,25 @@ def _exchange(send_left, send_right, plan, n_from_left, n_from_right):
     return from_left, from_right
 
 
-def _exchange_counts(n_left, n_right, plan, device):
-    """every rank learns how many rows its neighbours send it: returns (n_from_left, n_from_right)."""
+def _gather_stats(vec, plan):
+    """all ranks' small integer vectors: one collective and ONE device->host copy.  Returns int64 [world, k]."""
     if plan.world == 1:
-        return 0, 0
+        return vec.cpu()[None]
     if dist.get_backend() == "gloo":
-        device = "cpu"
-    mine = torch.tensor([n_left, n_right], dtype=torch.int64, device=device)
-    parts = [torch.empty_like(mine) for _ in range(plan.world)]
-    dist.all_gather(parts, mine)
-    allc = torch.stack(parts).cpu()
-    # my left neighbour sends me its send_right; my right neighbour sends me its send_left
-    return int(allc[plan.left, 1]), int(allc[plan.right, 0])
+        vec = vec.cpu()
+    out = torch.empty(plan.world * vec.numel(), dtype=vec.dtype, device=vec.device)
+    dist.all_gather_into_tensor(out, vec.contiguous())
+    return out.cpu().view(plan.world, -1)
+
+
+def _nonzero_n(mask, n):
+    """indices of the n set entries of mask without a device->host sync when the count is already known."""
+    if hasattr(torch, "nonzero_static"):
+        try:
+            return torch.nonzero_static(mask, size=n).flatten()
+        except (RuntimeError, NotImplementedError):
+            pass
+    return torch.nonzero(mask).flatten()
 
 
 class CudaBackend:
@@ -134,15 +156,22 @@ class CudaBackend:
 class SlabDomainMD:
     """Domain-decomposed MD state of one rank.  x in nm, v in nm/ps, f in kJ/mol/nm, masses in Da."""
 
-    def __init__(self, backend, plan, x_nm, v, mass, gid, feat=None):
+    def __init__(self, backend, plan, x_nm, v, mass, gid, feat=None, migrate_every=1):
+        """``migrate_every`` > 1 hands atoms over only every that many steps; in between an owner keeps integrating
+        atoms that have left its slab, which is exact as long as none strays further than ``plan.margin`` (checked
+        at every migration; the halo is that much wider)."""
+        if int(migrate_every) > 1 and plan.margin <= 0.0:
+            raise ValueError("migrate_every > 1 needs a SlabPlan with margin > 0")
         self.be, self.plan = backend, plan
         self.x, self.v, self.mass, self.gid, self.feat = x_nm, v, mass, gid, feat
         self.f = torch.zeros_like(self.x)
         self.n_halo = (0, 0)
+        self.migrate_every = int(migrate_every)
+        self._since_migration = 0
 
     # ---- construction ------------------------------------------------------------------------------
     @staticmethod
-    def scatter_global(backend, plan, x_nm_all, v_all, mass_all, device, feat_all=None):
+    def scatter_global(backend, plan, x_nm_all, v_all, mass_all, device, feat_all=None, migrate_every=1):
         """every rank holds the same global arrays (numpy) and keeps the atoms of its slab."""
         xw = np.mod(x_nm_all[:, 0] * 10.0, plan.box[0])
         own = np.clip(np.floor(xw / plan.width).astype(np.int64), 0, plan.world - 1) == plan.rank
@@ -150,30 +179,44 @@ class SlabDomainMD:
         t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)  # noqa: E731
         return SlabDomainMD(backend, plan, t(x_nm_all[own], torch.float64), t(v_all[own], torch.float64),
                             t(mass_all[own], torch.float64), t(gid, torch.int64),
-                            None if feat_all is None else t(feat_all[own], torch.float32))
+                            None if feat_all is None else t(feat_all[own], torch.float32),
+                            migrate_every=migrate_every)
 
     # ---- one step ------------------------------------------------------------------------------------
     def migrate(self):
-        """hand atoms that left the slab to the neighbour that now owns them."""
+        """hand atoms that left the slab to the neighbour that now owns them (one collective, one host sync)."""
         p = self.plan
+        self._since_migration = 0
         if p.world == 1:
             return
-        xw = p.wrap(self.x[:, 0] * 10.0)
-        d = (p.owner(xw) - p.rank) % p.world          # 0 stay, 1 -> right, world-1 -> left
-        go_r, go_l = d == 1, d == p.world - 1
+        dx = p.centered(self.x[:, 0] * 10.0)
+        half = 0.5 * p.width
+        go_r, go_l = dx >= half, dx < -half
         if p.world == 2:
-            go_l = torch.zeros_like(go_r)              # left and right are the same rank
-        stay = ~(go_r | go_l)
-        if bool(((d != 0) & ~(go_r | go_l)).any()):
-            raise RuntimeError("an atom moved further than one slab in a single step")
+            go_r, go_l = go_r | go_l, torch.zeros_like(go_l)     # left and right are the same rank
+        stray = dx.abs() - half
+        far = stray >= p.width                                    # beyond the adjacent slab
+        over = stray > p.margin + 1e-9 if self.migrate_every > 1 else torch.zeros_like(far)
+        mine = torch.stack([go_l.sum(), go_r.sum(), far.sum(), over.sum()])
+        table = _gather_stats(mine, p)
+        if int(table[:, 2].sum()):
+            raise RuntimeError("an atom moved further than one slab between two migrations")
+        if int(table[:, 3].sum()):
+            raise RuntimeError(f"an atom strayed more than the halo margin ({p.margin} A) out of its slab: "
+                               "migrate more often or widen the margin")
+        nl, nr = int(table[p.rank, 0]), int(table[p.rank, 1])
+        fl, fr = int(table[p.left, 1]), int(table[p.right, 0])    # left's send_right, right's send_left
+        if int(table[:, 0:2].sum()) == 0:
+            return
         cols = [self.x, self.v, self.mass[:, None], self.gid[:, None].to(torch.float64)]
         if self.feat is not None:
             cols.append(self.feat[:, None].to(torch.float64))
-        rows = torch.cat(cols, dim=1)
-        nl, nr = int(go_l.sum()), int(go_r.sum())
-        fl, fr = _exchange_counts(nl, nr, p, self.x.device)
-        got_l, got_r = _exchange(rows[go_l], rows[go_r], p, fl, fr)
-        rows = torch.cat([rows[stay], got_l, got_r])
+        # stayers first, then the rows for the left, then for the right neighbour (stable: stayers keep their order)
+        order = torch.argsort(go_l.to(torch.int8) + 2 * go_r.to(torch.int8), stable=True)
+        rows = torch.cat(cols, dim=1)[order]
+        n_stay = rows.shape[0] - nl - nr
+        got_l, got_r = _exchange(rows[n_stay:n_stay + nl], rows[n_stay + nl:], p, fl, fr)
+        rows = torch.cat([rows[:n_stay], got_l, got_r])
         self.x, self.v = rows[:, 0:3].contiguous(), rows[:, 3:6].contiguous()
         self.mass, self.gid = rows[:, 6].contiguous(), rows[:, 7].round().long()
         if self.feat is not None:
@@ -185,16 +228,17 @@ class SlabDomainMD:
         second half-kick is fused into the read-out."""
         p, be = self.plan, self.be
         pos = self.x * 10.0
-        xw = p.wrap(pos[:, 0])
         if p.world > 1:
-            to_l, to_r = p.halo_masks(xw)
-            idx_l = torch.nonzero(to_l).flatten().to(torch.int32)
-            idx_r = torch.nonzero(to_r).flatten().to(torch.int32)
+            to_l, to_r = p.halo_masks_centered(p.centered(pos[:, 0]))
+            table = _gather_stats(torch.stack([to_l.sum(), to_r.sum()]), p)      # the step's one host sync
+            idx_l = _nonzero_n(to_l, int(table[p.rank, 0])).to(torch.int32)
+            idx_r = _nonzero_n(to_r, int(table[p.rank, 1])).to(torch.int32)
+            fl, fr = int(table[p.left, 1]), int(table[p.right, 0])
         else:
             idx_l = idx_r = torch.zeros(0, dtype=torch.int32, device=pos.device)
+            fl = fr = 0
         cols = [pos] if self.feat is None else [pos, self.feat[:, None].to(torch.float64)]
         rows = torch.cat(cols, dim=1)
-        fl, fr = _exchange_counts(idx_l.shape[0], idx_r.shape[0], p, pos.device)
         h_l, h_r = _exchange(rows[idx_l.long()], rows[idx_r.long()], p, fl, fr)
         self.n_halo = (fl, fr)
         local = torch.cat([rows, h_l, h_r])
@@ -217,7 +261,9 @@ class SlabDomainMD:
         """first half-kick + drift, migration, halo exchange + forces, second half-kick."""
         self.v += (0.5 * dt) * self.f / self.mass[:, None]
         self.x += dt * self.v
-        self.migrate()
+        self._since_migration += 1
+        if self._since_migration >= self.migrate_every:
+            self.migrate()
         self.compute_forces(dt_kick=dt)
 
     def kinetic_energy(self):

@@ -129,3 +129,47 @@ def test_shard_replicas_partition():
 def test_slab_too_thin_is_rejected():
     with pytest.raises(ValueError):
         SlabPlan(27.27, 7.5, 8, 0)
+
+
+def _worker_lazy(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.Generator(np.random.PCG64(11))
+        n = 500
+        x = rng.uniform(0, BOX, (n, 3)) / 10.0
+        v = rng.standard_normal((n, 3)) * 0.5
+        m = np.full(n, 39.9)
+        plan = SlabPlan(BOX, RC, world, rank, margin=1.5)
+        md = SlabDomainMD.scatter_global(FakeBackend(), plan, x, v, m, "cpu", feat_all=np.arange(n, dtype=np.float32),
+                                         migrate_every=3)
+        md.compute_forces()
+        n_strays = 0
+        for step in range(7):
+            md.step(0.02)
+            gids = md.gather_by_gid(torch.ones(md.x.shape[0], 1), n)
+            assert torch.all(gids == 1.0), "atom lost or duplicated"
+            # owners may now hold atoms outside their slab; every owned atom must still see its whole neighbourhood
+            x_all = md.gather_by_gid(md.x, n).numpy() * 10.0
+            ref = onb.edges_jaxmd(x_all, BOX, RC)
+            mine = np.isin(ref[0], md.gid.numpy())
+            assert np.array_equal(onb.edge_set(md.be.local_edges_gid), onb.edge_set(ref[:, mine])), f"step {step}"
+            n_strays += int((plan.owner(plan.wrap(md.x[:, 0] * 10.0)) != rank).sum())
+        ret[rank] = n_strays
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_lazy_migration_keeps_neighbourhoods_complete(world):
+    """migrate_every = 3 with a 1.5 A halo margin: between migrations owners integrate atoms that have left their
+    slab (the test makes sure some have), and the local edge sets stay identical to the single-domain ones."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_lazy, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world and sum(ret.values()) > 0
+
+
+def test_lazy_migration_needs_margin():
+    with pytest.raises(ValueError):
+        SlabDomainMD(None, SlabPlan(BOX, RC, 2, 0), None, None, None, None, migrate_every=4)
