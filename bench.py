@@ -39,6 +39,9 @@ WORKLOADS = {
     "lj32k": dict(kind="lj", n_side=32, desc="LJ box 32,768 atoms, same density/cutoff"),
     "lj258": dict(kind="lj", n_side=None, desc="LJ argon 258 atoms (configs[0] fixture)"),
     "tip3p774": dict(kind="water", n_side=None, desc="TIP3P 258 molecules / 774 atoms (configs[1] fixture)"),
+    "lj258x1024": dict(kind="lj", n_side=None, n_frames=1024,
+                       desc="ensemble of 1024 independent LJ-258 replicas per GPU, block-diagonal batch "
+                            "(configs[4]: 8192 replicas over 8 GPUs)"),
     "tip4p4096": dict(kind="water", n_side=None, desc="TIP4P-Ew 4096 molecules, 16384 sites, 12288 GNN nodes, "
                                                          "virtual M site re-placed every step (configs[2])"),
 }
@@ -53,6 +56,12 @@ def build_system(name, seed=42):
     w = WORKLOADS[name]
     if name == "lj258":
         pos = np.load(os.path.join(FIX, "lj_init_pos.npy")).astype(np.float64)
+        return pos, 27.27, 7.5, np.full(len(pos), 39.9), "scaler_lj.npz", "lj", 100.0
+    if name == "lj258x1024":
+        # independent replicas: the fixture configuration with a different small displacement per replica
+        base = np.load(os.path.join(FIX, "lj_init_pos.npy")).astype(np.float64)
+        rng = np.random.Generator(np.random.PCG64(seed))
+        pos = (base[None] + 0.05 * rng.standard_normal((w["n_frames"],) + base.shape)).reshape(-1, 3)
         return pos, 27.27, 7.5, np.full(len(pos), 39.9), "scaler_lj.npz", "lj", 100.0
     if name == "tip3p774":
         pos = np.load(os.path.join(FIX, "water_init_pos.npy")).astype(np.float64)
@@ -265,7 +274,8 @@ def run_ours(args):
             tip4p.set_state(x4 / 10.0, v4)
             eng = tip4p.eng
         else:
-            eng = MDEngine(kind, sd, box, rc, m, s_np["mean"], s_np["var"], precision=prec, device=local)
+            eng = MDEngine(kind, sd, box, rc, m, s_np["mean"], s_np["var"], precision=prec, device=local,
+                           n_frames=WORKLOADS[args.workload].get("n_frames", 1))
             eng.set_state(pos / 10.0, maxwell_boltzmann(m, temp, 1234 + rank))
         ctx = eng.ctx
         n_edges = ctx.neighbor_count()
