@@ -223,7 +223,8 @@ def run_ours(args):
         plan = SlabPlan(box, rc, world, rank, margin=DD_MARGIN if world > 1 else 0.0)
         n_loc_cap = int((n_total / world) * (1.0 + 2.0 * plan.halo / plan.width) * 1.15) + 4096
         ctx.reserve(n_loc_cap, int(n_total / world * 1.1 + 4096) * 34)
-        md = SlabDomainMD.scatter_global(CudaBackend(ctx, box, rc, 4), plan, pos / 10.0,
+        md = SlabDomainMD.scatter_global(CudaBackend(ctx, box, rc, 4, overlap=os.environ.get("GAMD_DD_OVERLAP", "0") == "1"),
+                                         plan, pos / 10.0,
                                          maxwell_boltzmann(m, temp, 1234), m, f"cuda:{local}",
                                          migrate_every=DD_MIGRATE_EVERY if world > 1 else 1)
         md.compute_forces()

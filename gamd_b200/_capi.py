@@ -63,6 +63,9 @@ SIGNATURES = {
     "gamd_tip4p_unstrip": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_void_p]),
     "gamd_dd_begin": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_double), c_float, c_void_p, c_void_p]),
     "gamd_dd_layer": (c_int32, [c_void_p, c_int32, c_void_p]),
+    "gamd_dd_split_tiles": (c_int32, [c_void_p, c_void_p]),
+    "gamd_dd_layer_edges": (c_int32, [c_void_p, c_int32, c_int32, c_void_p]),
+    "gamd_dd_layer_nodes": (c_int32, [c_void_p, c_int32, c_void_p]),
     "gamd_dd_pack_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "gamd_dd_unpack_rows": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "gamd_dd_finish": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p]),
@@ -128,6 +131,7 @@ class Context:
         if rc:
             raise GamdError(rc, self.lib.gamd_last_error(None).decode())
         self.device = device
+        self.precision = int(precision)
         self.cap_atoms = 0
         self.cap_edges = 0
 
@@ -247,6 +251,15 @@ class Context:
 
     def dd_layer(self, layer):
         self._check(self.lib.gamd_dd_layer(self._h, int(layer), _stream()))
+
+    def dd_split_tiles(self):
+        self._check(self.lib.gamd_dd_split_tiles(self._h, _stream()))
+
+    def dd_layer_edges(self, layer, which=-1):
+        self._check(self.lib.gamd_dd_layer_edges(self._h, int(layer), int(which), _stream()))
+
+    def dd_layer_nodes(self, layer):
+        self._check(self.lib.gamd_dd_layer_nodes(self._h, int(layer), _stream()))
 
     def dd_pack_rows(self, local_idx_i32, out):
         self._check(self.lib.gamd_dd_pack_rows(self._h, _ptr(local_idx_i32), local_idx_i32.shape[0], _ptr(out), _stream()))

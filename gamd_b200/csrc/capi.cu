@@ -106,6 +106,9 @@ void carve(gamd_ctx* ctx, Carver& c, int64_t A, int64_t E) {
   ctx->pd = c.take<float>((size_t)A * GAMD_NF);
   ctx->agg = c.take<float>((size_t)A * GAMD_NF);
   ctx->part = c.take<float>((size_t)(E / 32 + 4) * 2 * GAMD_NF);
+  ctx->tile_list[0] = c.take<int>(E / 128 + 4);
+  ctx->tile_list[1] = c.take<int>(E / 128 + 4);
+  ctx->tile_count = c.take<int>(4);
   ctx->pred = c.take<float>((size_t)A * 3);
   ctx->feat_s = c.take<float>(A);
   ctx->stage_a = c.take<double>((size_t)A * 3);
@@ -837,6 +840,56 @@ int gamd_dd_layer(gamd_ctx* ctx, int32_t layer, void* stream) {
   if (rc) return rc;
   if (ctx->dd_n_loc <= 0 || layer < 0 || layer >= ctx->mw.n_layers) return GAMD_EINVAL;
   return model_layer(ctx, layer, ctx->pos_feat_s, ctx->dd_n_loc, (cudaStream_t)stream);
+}
+
+// one warp per 128-edge tile of the CSR: does any edge of the tile have a halo atom (local index >= n_own) as its
+// source?  Tiles are appended to the interior (0) or boundary (1) list; the order inside a list does not matter
+// (every tile writes its own receiver rows / partial-sum blocks).
+__global__ void k_dd_split_tiles(const int* __restrict__ col, const int* __restrict__ perm,
+                                 const int* __restrict__ n_edges, int n_own, int* __restrict__ list0,
+                                 int* __restrict__ list1, int* __restrict__ counts) {
+  const int tile = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int E = *n_edges;
+  if ((int64_t)tile * 128 >= E) return;
+  bool halo = false;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int e = tile * 128 + k * 32 + lane;
+    if (e < E) halo |= perm[col[e]] >= n_own;
+  }
+  halo = __any_sync(0xffffffffu, halo);
+  if (lane == 0) {
+    const int i = atomicAdd(counts + (halo ? 1 : 0), 1);
+    (halo ? list1 : list0)[i] = tile;
+  }
+}
+
+int gamd_dd_split_tiles(gamd_ctx* ctx, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (ctx->dd_n_loc <= 0) return GAMD_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  GAMD_CUDA(cudaMemsetAsync(ctx->tile_count, 0, 4 * sizeof(int), st));
+  const int64_t max_tiles = ctx->cap_edges / 128 + 1;
+  k_dd_split_tiles<<<ceil_div(max_tiles * 32, 256), 256, 0, st>>>(ctx->col_idx, ctx->perm, ctx->n_edges,
+                                                                   (int)ctx->dd_n_own, ctx->tile_list[0],
+                                                                   ctx->tile_list[1], ctx->tile_count);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int gamd_dd_layer_edges(gamd_ctx* ctx, int32_t layer, int32_t which, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (ctx->dd_n_loc <= 0 || layer < 0 || layer >= ctx->mw.n_layers || which < -1 || which > 1) return GAMD_EINVAL;
+  return model_layer_edges(ctx, layer, (cudaStream_t)stream, which);
+}
+
+int gamd_dd_layer_nodes(gamd_ctx* ctx, int32_t layer, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (ctx->dd_n_loc <= 0 || layer < 0 || layer >= ctx->mw.n_layers) return GAMD_EINVAL;
+  return model_layer_nodes(ctx, layer, ctx->pos_feat_s, ctx->dd_n_loc, (cudaStream_t)stream);
 }
 
 int gamd_dd_pack_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, float* d_out, void* stream) {

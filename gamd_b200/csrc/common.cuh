@@ -103,6 +103,9 @@ struct gamd_ctx {
   bool use_graphs = true;
   int64_t graph_launches_per_step = 0, launches_last_step = 0;
   int64_t dd_n_own = 0, dd_n_loc = 0;   // domain decomposition: owned / owned + halo atoms of the step in flight
+  // 128-edge tiles split by "has a halo source": [0] interior, [1] boundary (lists + device counters)
+  int* tile_list[2] = {nullptr, nullptr};
+  int* tile_count = nullptr;
   int sm_count = 148;
 
   // optional per-stage CUDA-event timers (gamd_profile_enable / gamd_profile_read)
@@ -148,13 +151,16 @@ int nbr_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float* d_dist, f
 int csr_from_sorted_coo(gamd_ctx* ctx, const int64_t* d_center, const int64_t* d_neigh, int64_t n_atoms, int64_t n_edges, cudaStream_t st);
 int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cudaStream_t st);
 
-int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st);
+// which: -1 every tile; 0 / 1 only the interior / boundary tiles of the domain-decomposition split (ctx->tile_list)
+int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which = -1);
 int node_update_tc_launch(gamd_ctx* ctx, int mode, int layer, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int atoms_per_frame,
                           const float box[3], cudaStream_t st);
 int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64_t n_atoms, int atoms_per_frame,
                 const float box[3], cudaStream_t st);
 int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
+int model_layer_edges(gamd_ctx* ctx, int l, cudaStream_t st, int which);
+int model_layer_nodes(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* feat, const int* orig_id,
                        int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st);
 

@@ -585,26 +585,37 @@ int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64
   return 0;
 }
 
-// message-passing layer l: edge chain + segmented sum, then the node update (next layer's LN + affines, or the
-// force decoder after the last layer)
-int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st) {
+// message-passing layer l, edge part: edge chain + segmented sum (which: -1 all tiles, 0 / 1 the interior / boundary
+// tiles of the domain-decomposition split - tensor-core path only)
+int model_layer_edges(gamd_ctx* ctx, int l, cudaStream_t st, int which) {
   const ModelW& mw = ctx->mw;
-  const int grid_edge = ctx->sm_count * 3;
+  const bool tcpath = ctx->desc.precision != GAMD_PREC_FP32;
+  if (!tcpath && which >= 0) {
+    ctx->err = "tile-split layers need a tensor-core precision (bf16x3 / bf16)";
+    return GAMD_EUNSUPPORTED;
+  }
+  prof_mark(ctx, "mp_edge", st);
+  if (tcpath) {
+    int rc = mp_edge_tc_launch(ctx, l, st, which);
+    if (rc) return rc;
+  } else {
+    k_mp_edge<<<ctx->sm_count * 3, NT, sizeof(Smem), st>>>(mw.layer[l], ctx->e_emb, ctx->row_ptr, ctx->col_idx,
+                                                            ctx->edge_dst, ctx->n_edges, ctx->hn, ctx->srcA, ctx->dstA,
+                                                            ctx->agg, ctx->part);
+    GAMD_LAUNCH_CHECK();
+  }
+  prof_mark(ctx, "mp_edge", st);
+  return 0;
+}
+
+// message-passing layer l, node part: next layer's LN + affines, or the force decoder after the last layer
+int model_layer_nodes(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st) {
+  const ModelW& mw = ctx->mw;
   const int node_tiles = ceil_div(n_atoms, TM);
   const int grid_node = node_tiles < ctx->sm_count * 3 ? node_tiles : ctx->sm_count * 3;
   const size_t smem = sizeof(Smem);
   const bool tcpath = ctx->desc.precision != GAMD_PREC_FP32;
   const int agg_tile = tcpath ? 32 : GAMD_EDGE_TILE;
-  prof_mark(ctx, "mp_edge", st);
-  if (tcpath) {
-    int rc = mp_edge_tc_launch(ctx, l, st);
-    if (rc) return rc;
-  } else {
-    k_mp_edge<<<grid_edge, NT, smem, st>>>(mw.layer[l], ctx->e_emb, ctx->row_ptr, ctx->col_idx, ctx->edge_dst,
-                                           ctx->n_edges, ctx->hn, ctx->srcA, ctx->dstA, ctx->agg, ctx->part);
-    GAMD_LAUNCH_CHECK();
-  }
-  prof_mark(ctx, "mp_edge", st);
   prof_mark(ctx, "node_update", st);
   NodeArgs na = node_args(mw);
   na.cur = mw.layer[l];
@@ -627,6 +638,12 @@ int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, c
   GAMD_LAUNCH_CHECK();
   prof_mark(ctx, "node_update", st);
   return 0;
+}
+
+int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st) {
+  int rc = model_layer_edges(ctx, l, st, -1);
+  if (rc) return rc;
+  return model_layer_nodes(ctx, l, pos_feat, n_atoms, st);
 }
 
 int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*feat*/, const int* orig_id,

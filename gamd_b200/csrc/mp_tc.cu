@@ -47,13 +47,11 @@ struct MpTcArgs {
   const int *row_ptr, *col, *edst, *n_edges;
   const float *hn, *srcA, *dstA;
   float *agg, *part;
+  const int *tile_list, *n_list;   // optional: process only these tiles (domain decomposition: interior / boundary)
   int exact;
   long long* dbg;   // development: clock64 timeline of CTA 0 (nullptr = off)
 };
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -296,7 +294,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
   SmemTC& sm = *reinterpret_cast<SmemTC*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int E = *a.n_edges;
-  const int ntiles = (E + TILE - 1) / TILE;
+  // tiles are addressed by SLOT: slot -> tile is the identity, or a look-up in the caller's tile list
+  const int ntiles = a.tile_list ? *a.n_list : (E + TILE - 1) / TILE;
   const int npairs = (ntiles + 1) / 2;
 
   if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base, 512);
@@ -344,17 +343,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
     int dbg_n = 0;
     // endpoints of my edge in the first tile; the next tile's are fetched while the current one is processed
     int nsrc = 0, ndst = -1;
+    int next_tile = -1;
     {
-      const int t0 = blockIdx.x * 2 + g;
-      const int e_first = t0 * TILE + r;
-      if (t0 < ntiles && e_first < E) {
+      const int s0 = blockIdx.x * 2 + g;
+      if (s0 < ntiles) next_tile = a.tile_list ? __ldg(a.tile_list + s0) : s0;
+      const int e_first = next_tile * TILE + r;
+      if (next_tile >= 0 && e_first < E) {
         nsrc = a.col[e_first];
         ndst = a.edst[e_first];
       }
     }
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int tile = pair * 2 + g;
-      if (tile >= ntiles) continue;
+      const int slot = pair * 2 + g;
+      if (slot >= ntiles) continue;
+      const int tile = next_tile;
       const bool dbg_on = dbg_rec && blockIdx.x == 0 && lane == 0 && dbg_n + 14 <= 256;
       if (dbg_on) dbg_rec[dbg_n++] = clock64();
       const int e0 = tile * TILE;
@@ -367,12 +369,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
       uint4 q[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) q[i] = __ldg(bh + i * 128);
-      {  // endpoints of my edge in the next tile of this slot
-        const int ntile = tile + 2 * (int)gridDim.x;
-        const int en = ntile * TILE + r;
+      {  // the next tile of this slot and the endpoints of my edge in it
+        const int nslot = slot + 2 * (int)gridDim.x;
+        next_tile = -1;
+        if (nslot < ntiles) next_tile = a.tile_list ? __ldg(a.tile_list + nslot) : nslot;
+        const int en = next_tile * TILE + r;
         nsrc = 0;
         ndst = -1;
-        if (ntile < ntiles && en < E) {
+        if (next_tile >= 0 && en < E) {
           nsrc = a.col[en];
           ndst = a.edst[en];
         }
@@ -380,8 +384,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
       c.dst_row = reinterpret_cast<const float4*>(a.dstA + (size_t)(dst < 0 ? 0 : dst) * 128 + c.col0);
       issue_gather(c, 0);
       {  // pull my share of the NEXT tile's e blob into L2 while this tile is being processed
-        const int ntile = tile + 2 * (int)gridDim.x;
-        if (ntile < ntiles && (lane & 7) == 0) {
+        const int ntile = next_tile;
+        if (ntile >= 0 && (lane & 7) == 0) {
           const uint8_t* nb = a.e_blob + (size_t)ntile * 65536 + ((size_t)(ch * 8) * 128 + r) * 16;
 #pragma unroll
           for (int i = 0; i < 8; i++) {
@@ -559,7 +563,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
 
 }  // namespace
 
-int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st) {
+int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which) {
   static bool attr_done = false;
   const size_t smem = sizeof(SmemTC) + 1024;
   if (!attr_done) {
@@ -579,9 +583,14 @@ int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st) {
   a.dstA = ctx->dstA;
   a.agg = ctx->agg;
   a.part = ctx->part;
+  a.tile_list = which >= 0 ? ctx->tile_list[which] : nullptr;
+  a.n_list = which >= 0 ? ctx->tile_count + which : nullptr;
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
   a.dbg = (getenv("GAMD_TIMELINE") && layer == 1) ? reinterpret_cast<long long*>(ctx->e_emb + (size_t)ctx->cap_edges * 128) : nullptr;
-  k_mp_edge_tc<<<ctx->sm_count, THREADS, smem, st>>>(a);
+  // interior launch of a tile-split layer: optionally leave a few SMs to the halo exchange running beside it
+  static const int reserve = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
+  const int grid = which == 0 && reserve > 0 && reserve < ctx->sm_count ? ctx->sm_count - reserve : ctx->sm_count;
+  k_mp_edge_tc<<<grid, THREADS, smem, st>>>(a);
   GAMD_LAUNCH_CHECK();
   return 0;
 }

@@ -18,6 +18,8 @@ The host logic (slab ownership, migration, halo selection, message pairing) is p
 agnostic: ``tests/test_dist_cpu.py`` runs it with the ``gloo`` backend, world size 2, on CPU tensors with a
 fake compute backend.  The CUDA backend calls ``gamd_dd_*`` through the C ABI.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -128,9 +130,14 @@ def _nonzero_n(mask, n):
 class CudaBackend:
     """Force evaluation on owned + halo atoms through the C ABI (``gamd_dd_*``)."""
 
-    def __init__(self, ctx, box, cutoff, n_layers):
+    def __init__(self, ctx, box, cutoff, n_layers, overlap=False):
         self.ctx, self.box, self.cutoff, self.n_layers = ctx, box, cutoff, n_layers
         self.row_width = 256
+        # tile-split layers (halo exchange underneath the interior edge work) exist for the tensor-core paths.  Off by
+        # default: measured on 2 and 4 B200 the persistent edge kernel leaves no SM to the NCCL kernel beside it, so
+        # nothing overlaps and the two launches per layer cost 1-2 % (profiles/experiments/README.md)
+        from . import _capi
+        self.split_layers = bool(overlap) and ctx.precision != _capi.PREC_FP32
 
     def begin(self, pos_local, n_own, feat_local):
         n_loc = pos_local.shape[0]
@@ -140,6 +147,15 @@ class CudaBackend:
 
     def layer(self, l):
         self.ctx.dd_layer(l)
+
+    def split_tiles(self):
+        self.ctx.dd_split_tiles()
+
+    def edges(self, l, which):
+        self.ctx.dd_layer_edges(l, which)
+
+    def nodes(self, l):
+        self.ctx.dd_layer_nodes(l)
 
     def pack(self, idx_i32):
         out = torch.empty((idx_i32.shape[0], self.row_width), dtype=torch.float32, device=idx_i32.device)
@@ -246,16 +262,46 @@ class SlabDomainMD:
         feat_local = None if self.feat is None else local[:, 3].float().contiguous()
         n_own = pos.shape[0]
         be.begin(pos_local, n_own, feat_local)
-        for l in range(be.n_layers):
-            be.layer(l)
-            if l + 1 < be.n_layers and p.world > 1:
-                r_l, r_r = _exchange(be.pack(idx_l), be.pack(idx_r), p, fl, fr)
-                be.unpack(n_own, r_l)
-                be.unpack(n_own + fl, r_r)
+        force_split = os.environ.get("GAMD_DD_FORCE_SPLIT") == "1"      # measurement aid: split path on one rank
+        if (p.world > 1 or force_split) and getattr(be, "split_layers", False) and pos.is_cuda:
+            self._layers_overlapped(idx_l, idx_r, fl, fr, n_own)
+        else:
+            for l in range(be.n_layers):
+                be.layer(l)
+                if l + 1 < be.n_layers and p.world > 1:
+                    r_l, r_r = _exchange(be.pack(idx_l), be.pack(idx_r), p, fl, fr)
+                    be.unpack(n_own, r_l)
+                    be.unpack(n_own + fl, r_r)
         if dt_kick is None:
             be.finish(self.f, None, None, 0.0)
         else:
             be.finish(self.f, self.v, self.mass, dt_kick)
+
+    def _layers_overlapped(self, idx_l, idx_r, fl, fr, n_own):
+        """the message-passing layers with the halo exchange hidden: the rows a layer's node update produced are
+        packed, sent and unpacked on a side stream while the main stream already runs the next layer's edge chain on
+        the tiles that have no halo source (typically 2/3 of them); only the boundary tiles wait for the exchange."""
+        p, be = self.plan, self.be
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        be.split_tiles()
+        be.edges(0, -1)                 # layer 0: its node inputs are position independent, no halo rows needed
+        be.nodes(0)
+        for l in range(1, be.n_layers):
+            side.wait_stream(main)      # rows of node update l-1 are complete
+            with torch.cuda.stream(side):
+                s_l, s_r = be.pack(idx_l), be.pack(idx_r)
+                r_l, r_r = _exchange(s_l, s_r, p, fl, fr)
+                be.unpack(n_own, r_l)
+                be.unpack(n_own + fl, r_r)
+                for t in (s_l, s_r, r_l, r_r):
+                    t.record_stream(side)
+            be.edges(l, 0)              # interior tiles: owned sources only
+            main.wait_stream(side)
+            be.edges(l, 1)              # boundary tiles: read the refreshed halo rows
+            be.nodes(l)
 
     def step(self, dt):
         """first half-kick + drift, migration, halo exchange + forces, second half-kick."""

@@ -188,6 +188,13 @@ int gamd_tip4p_unstrip(gamd_ctx* ctx, const double* d_a3, double* d_a4, int64_t 
  *   gamd_dd_begin   local atoms = n_own owned + (n_local - n_own) halo atoms (neighbours only: no CSR row);
  *                   neighbor search with the GLOBAL periodic box, edge encoder, layer-0 node prologue
  *   gamd_dd_layer   message-passing layer `layer` + node update (decoder after the last layer)
+ *   gamd_dd_split_tiles / gamd_dd_layer_edges / gamd_dd_layer_nodes   the same layer in pieces, so that the halo
+ *                   exchange of layer l-1's rows can run (on another stream) underneath most of layer l's edge work:
+ *                   split_tiles (once per step, after gamd_dd_begin) sorts the 128-edge tiles of the CSR into
+ *                   "interior" (no halo source) and "boundary"; layer_edges(which = 0) runs the edge chain of
+ *                   nn_module.py:135-142 on the interior tiles and needs no halo row, layer_edges(which = 1) the
+ *                   rest (after gamd_dd_unpack_rows); layer_nodes finishes the layer (nn_module.py:143-148).
+ *                   which = -1 runs every tile.  Tensor-core precisions only (GAMD_EUNSUPPORTED for fp32).
  *   gamd_dd_pack_rows / gamd_dd_unpack_rows   rows [hn | src_affine(hn)] (2 x 128 fp32) of the listed owned
  *                   atoms -> send buffer; received rows -> the halo atoms first_local_idx .. +n-1.  The caller
  *                   moves the buffers between ranks (NCCL send/recv over NVLink) after layers 0 .. L-2.
@@ -196,6 +203,9 @@ int gamd_tip4p_unstrip(gamd_ctx* ctx, const double* d_a3, double* d_a4, int64_t 
 int gamd_dd_begin(gamd_ctx* ctx, const double* d_pos, int64_t n_own, int64_t n_local, const double h_box[3],
                   float cutoff, const float* d_feat, void* stream);
 int gamd_dd_layer(gamd_ctx* ctx, int32_t layer, void* stream);
+int gamd_dd_split_tiles(gamd_ctx* ctx, void* stream);
+int gamd_dd_layer_edges(gamd_ctx* ctx, int32_t layer, int32_t which, void* stream);
+int gamd_dd_layer_nodes(gamd_ctx* ctx, int32_t layer, void* stream);
 int gamd_dd_pack_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, float* d_out, void* stream);
 int gamd_dd_unpack_rows(gamd_ctx* ctx, int64_t first_local_idx, int64_t n, const float* d_in, void* stream);
 int gamd_dd_finish(gamd_ctx* ctx, double* d_force, double* d_v, const double* d_mass, double dt, double* d_ke,

@@ -30,7 +30,7 @@ def _system():
     return pos, L, m, maxwell_boltzmann(m, 100.0, 77)
 
 
-def _worker(rank, world, port, precision, ret, migrate_every=1, margin=0.0):
+def _worker(rank, world, port, precision, ret, migrate_every=1, margin=0.0, overlap=False):
     from gamd_b200 import _capi
     from gamd_b200.dist import CudaBackend, SlabDomainMD, SlabPlan
     from gamd_b200.weights import random_state_dict
@@ -49,7 +49,7 @@ def _worker(rank, world, port, precision, ret, migrate_every=1, margin=0.0):
         ctx.finalize()
         ctx.reserve(n, n * 40)
         plan = SlabPlan(L, 7.5, world, rank, margin=margin)
-        md = SlabDomainMD.scatter_global(CudaBackend(ctx, L, 7.5, 4), plan, pos / 10.0, v0, m, f"cuda:{dev}",
+        md = SlabDomainMD.scatter_global(CudaBackend(ctx, L, 7.5, 4, overlap=overlap), plan, pos / 10.0, v0, m, f"cuda:{dev}",
                                          migrate_every=migrate_every)
         md.compute_forces()
         ctx.check_async_errors()
@@ -107,6 +107,19 @@ def test_slab_md_lazy_migration_equals_single_domain():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(3, _free_port(), _capi.PREC_BF16X3, ret, 3, 0.3), nprocs=3, join=True)
+    assert np.abs(ret["f0"] - f_ref).max() / np.abs(f_ref).max() <= 1e-4
+    assert np.abs(ret["x5"] - x_ref).max() <= 1e-7
+    assert abs(ret["ke"] - ke_ref) / ke_ref <= 1e-6
+
+
+def test_slab_md_split_layers_equals_single_domain():
+    """world 3 with the tile-split layer schedule (gamd_dd_split_tiles / _layer_edges / _layer_nodes: interior tiles
+    run while the halo rows travel on a side stream, boundary tiles after the unpack): same trajectory."""
+    from gamd_b200 import _capi
+    f_ref, x_ref, ke_ref = _reference(_capi.PREC_BF16X3)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(3, _free_port(), _capi.PREC_BF16X3, ret, 1, 0.0, True), nprocs=3, join=True)
     assert np.abs(ret["f0"] - f_ref).max() / np.abs(f_ref).max() <= 1e-4
     assert np.abs(ret["x5"] - x_ref).max() <= 1e-7
     assert abs(ret["ke"] - ke_ref) / ke_ref <= 1e-6
