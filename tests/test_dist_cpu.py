@@ -173,3 +173,25 @@ def test_lazy_migration_keeps_neighbourhoods_complete(world):
 def test_lazy_migration_needs_margin():
     with pytest.raises(ValueError):
         SlabDomainMD(None, SlabPlan(BOX, RC, 2, 0), None, None, None, None, migrate_every=4)
+
+
+def test_single_rank_stats_and_index_helpers():
+    """the two helpers that keep a domain-decomposed step at one host sync work without a process group."""
+    from gamd_b200.dist import _gather_stats, _nonzero_n
+    plan = SlabPlan(BOX, RC, 1, 0)
+    t = _gather_stats(torch.tensor([3, 5]), plan)
+    assert t.shape == (1, 2) and t.tolist() == [[3, 5]]
+    mask = torch.tensor([False, True, True, False, True])
+    assert _nonzero_n(mask, 3).tolist() == [1, 2, 4]
+
+
+def test_centered_offsets_handle_the_periodic_boundary():
+    """slab 0 of 4 spans [0, 10) A: an atom at x = 39.5 (just left of the box origin) is 0.5 A outside its left face,
+    not 29.5 A to the right; the halo masks send it to the left neighbour (the halo, 8.5 A, is wider than half the
+    10 A slab, so the atom in the middle goes both ways)."""
+    plan = SlabPlan(BOX, RC, 4, 0, margin=1.0)
+    dx = plan.centered(torch.tensor([39.5, 0.2, 5.0, 9.9, 10.4]))
+    assert torch.allclose(dx, torch.tensor([-5.5, -4.8, 0.0, 4.9, 5.4]))
+    to_l, to_r = plan.halo_masks_centered(dx)
+    assert to_l.tolist() == [True, True, True, False, False]
+    assert to_r.tolist() == [False, False, True, True, True]
