@@ -171,8 +171,9 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     sample = "lj32k" if args.workload == "lj1m" else args.workload
-    steps = max(1, min(args.steps, 3)) if sample == "lj32k" else args.steps
-    warm = min(args.warmup, 1) if sample == "lj32k" else args.warmup
+    # one oracle step on the 32,768-atom sample is ~2 s on 16 threads: K is honoured up to 30 steps (about a minute)
+    steps = max(1, min(args.steps, 30)) if sample == "lj32k" else args.steps
+    warm = min(args.warmup, 3) if sample == "lj32k" else args.warmup
     val, n, sps = oracle_steps(sample, steps, warm, threads)
     desc = f"{WORKLOADS[sample]['desc']}: {steps} NVE steps of the CPU oracle (torch CPU fp32 + numpy), {threads} threads"
     line = {
@@ -396,7 +397,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = "lj32k" if args.workload == "lj1m" else args.workload
-        k = 2 if sample == "lj32k" else 20
+        k = 5 if sample == "lj32k" else 20      # about 10 s of CPU work
         val, nn, sps = oracle_steps(sample, k, 1, threads)
         line["cpu_baseline"] = {"value": val, "unit": "atom-steps/s", "cores": threads, "kind": "port",
                                 "sample": f"{WORKLOADS[sample]['desc']}: {k} NVE steps of the CPU oracle "
