@@ -134,6 +134,17 @@ int check_ready(gamd_ctx* ctx) {
     ctx->err = "no scratch reserved: call gamd_reserve";
     return GAMD_ESTATE;
   }
+  GAMD_ENTER(ctx);
+  return 0;
+}
+
+// the bond table is indexed by frame-local atom id: it must cover exactly one frame
+int check_bonds(gamd_ctx* ctx, int64_t n_atoms, int n_frames) {
+  if (ctx->desc.use_bond && n_frames > 0 && n_atoms / n_frames != ctx->bond_atoms) {
+    ctx->err = "bond table was built for " + std::to_string(ctx->bond_atoms) + " atoms per frame, got " +
+               std::to_string(n_atoms / n_frames) + ": call gamd_set_bonds for this system";
+    return GAMD_EINVAL;
+  }
   return 0;
 }
 
@@ -141,13 +152,14 @@ int positions_to_forces(gamd_ctx* ctx, const double* d_x, double scale, int64_t 
                         float cutoff, const float* d_feat, cudaStream_t st) {
   float boxf[3] = {(float)box[0], (float)box[1], (float)box[2]};
   NbrParams p;
-  int rc = nbr_setup_params(ctx, n, n_frames, boxf, cutoff, GAMD_NBR_LT | GAMD_NBR_SELF, &p);
+  int rc = check_bonds(ctx, n, n_frames);
   if (rc) return rc;
+  if ((rc = nbr_setup_params(ctx, n, n_frames, boxf, cutoff, GAMD_NBR_LT | GAMD_NBR_SELF, &p))) return rc;
   prof_mark(ctx, "neighbor", st);
   if ((rc = nbr_bin_f64(ctx, d_x, scale, box, p, st))) return rc;
   if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
   prof_mark(ctx, "neighbor", st);
-  return model_forward_fp32(ctx, ctx->pos_feat_s, nullptr, ctx->perm, n, p.atoms_per_frame, boxf, st);
+  return model_forward(ctx, ctx->pos_feat_s, nullptr, ctx->perm, n, p.atoms_per_frame, boxf, st);
 }
 
 }  // namespace
@@ -235,6 +247,9 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   ctx->device = device;
   ctx->desc = *desc;
   ctx->use_graphs = getenv("GAMD_NO_GRAPH") == nullptr;
+  ctx->dbg_timeline = getenv("GAMD_TIMELINE") != nullptr;
+  ctx->dd_reserve_sms = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
+  ctx->mp_variant = getenv("GAMD_MP_VARIANT") ? atoi(getenv("GAMD_MP_VARIANT")) : 0;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   *out = ctx;
@@ -591,6 +606,7 @@ int gamd_neighbor_build(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, int3
     ctx->err = "no scratch reserved: call gamd_reserve";
     return GAMD_ESTATE;
   }
+  GAMD_ENTER(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   float boxf[3] = {(float)h_box[0], (float)h_box[1], (float)h_box[2]};
   NbrParams p;
@@ -628,10 +644,11 @@ int gamd_model_forward(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, int32
     return GAMD_EINVAL;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = check_bonds(ctx, n_atoms, n_frames))) return rc;
   if ((rc = csr_from_sorted_coo(ctx, d_center, d_neigh, n_atoms, n_edges, st))) return rc;
   if ((rc = pack_pos_feat(ctx, d_pos, d_feat, n_atoms, ctx->pos_feat_s, st))) return rc;
   float boxf[3] = {(float)h_box[0], (float)h_box[1], (float)h_box[2]};
-  if ((rc = model_forward_fp32(ctx, ctx->pos_feat_s, nullptr, nullptr, n_atoms, (int)(n_atoms / n_frames), boxf, st)))
+  if ((rc = model_forward(ctx, ctx->pos_feat_s, nullptr, nullptr, n_atoms, (int)(n_atoms / n_frames), boxf, st)))
     return rc;
   GAMD_CUDA(cudaMemcpyAsync(d_out, ctx->pred, sizeof(float) * 3 * n_atoms, cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -675,12 +692,14 @@ int gamd_compute_forces_host(gamd_ctx* ctx, const double* h_pos, int64_t n_atoms
 int gamd_vv_first_half(gamd_ctx* ctx, double* d_x, double* d_v, const double* d_f, const double* d_mass,
                        int64_t n_atoms, double dt, void* stream) {
   if (!ctx || !d_x || !d_v || !d_f || !d_mass || n_atoms <= 0) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
   return integ_first_half(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, (cudaStream_t)stream);
 }
 
 int gamd_vv_second_half(gamd_ctx* ctx, double* d_v, const double* d_f, const double* d_mass, int64_t n_atoms,
                         double dt, void* stream) {
   if (!ctx || !d_v || !d_f || !d_mass || n_atoms <= 0) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
   return integ_second_half(ctx, d_v, d_f, d_mass, n_atoms, dt, (cudaStream_t)stream);
 }
 
@@ -723,7 +742,7 @@ int gamd_md_run(gamd_ctx* ctx, double* d_x, double* d_v, double* d_f, const doub
     for (int d = 0; d < 3; d++) { memcpy(&bits, &h_box[d], 8); mix(bits); }
     memcpy(&bits, &dt, 8); mix(bits);
     uint32_t cb; memcpy(&cb, &cutoff, 4); mix(cb);
-    mix((uint64_t)ctx->scaler_var * 0 + (uint64_t)ctx->finalized);
+    // (scaler, weights, bonds: gamd_set_scaler / gamd_finalize_weights / gamd_set_bonds reset graph_key themselves)
     if (!ctx->graph_stream) {
       GAMD_CUDA(cudaStreamCreateWithFlags(&ctx->graph_stream, cudaStreamNonBlocking));
       GAMD_CUDA(cudaEventCreateWithFlags(&ctx->graph_ev_in, cudaEventDisableTiming));
@@ -803,12 +822,14 @@ int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, cons
 
 int gamd_tip4p_strip(gamd_ctx* ctx, const double* d_x4, double* d_x3, int64_t n_mol, void* stream) {
   if (!ctx || !d_x4 || !d_x3 || n_mol <= 0) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
   return integ_tip4p_strip(ctx, d_x4, d_x3, n_mol, (cudaStream_t)stream);
 }
 
 int gamd_tip4p_unstrip(gamd_ctx* ctx, const double* d_a3, double* d_a4, int64_t n_mol, double w_o, double w_h,
                        int32_t place_m, void* stream) {
   if (!ctx || !d_a3 || !d_a4 || n_mol <= 0) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
   return integ_tip4p_unstrip(ctx, d_a3, d_a4, n_mol, w_o, w_h, place_m, (cudaStream_t)stream);
 }
 
@@ -820,6 +841,11 @@ int gamd_dd_begin(gamd_ctx* ctx, const double* d_pos, int64_t n_own, int64_t n_l
   if (ctx->desc.kind != GAMD_MODEL_LJ && !d_feat) {
     ctx->err = "this model needs the node feature vector";
     return GAMD_EINVAL;
+  }
+  if (ctx->desc.use_bond) {
+    // the bond flag is looked up by frame-local atom id; a rank's local numbering is not the global one
+    ctx->err = "domain decomposition of a model with the bond flag is not built (bond look-up needs global atom ids)";
+    return GAMD_EUNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
   float boxf[3] = {(float)h_box[0], (float)h_box[1], (float)h_box[2]};
@@ -895,6 +921,7 @@ int gamd_dd_layer_nodes(gamd_ctx* ctx, int32_t layer, void* stream) {
 int gamd_dd_pack_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, float* d_out, void* stream) {
   if (!ctx || ctx->dd_n_loc <= 0 || n < 0 || (n > 0 && (!d_local_idx || !d_out))) return GAMD_EINVAL;
   if (n == 0) return 0;
+  GAMD_ENTER(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   k_dd_pack<<<ceil_div(n * 32, 256), 256, 0, st>>>(d_local_idx, ctx->inv_perm, n, ctx->hn, ctx->srcA, d_out);
   GAMD_LAUNCH_CHECK();
@@ -906,6 +933,7 @@ int gamd_dd_unpack_rows(gamd_ctx* ctx, int64_t first_local_idx, int64_t n, const
       (n > 0 && !d_in))
     return GAMD_EINVAL;
   if (n == 0) return 0;
+  GAMD_ENTER(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   k_dd_unpack<<<ceil_div(n * 32, 256), 256, 0, st>>>(first_local_idx, ctx->inv_perm, n, d_in, ctx->hn, ctx->srcA);
   GAMD_LAUNCH_CHECK();
@@ -915,6 +943,7 @@ int gamd_dd_unpack_rows(gamd_ctx* ctx, int64_t first_local_idx, int64_t n, const
 int gamd_dd_finish(gamd_ctx* ctx, double* d_force, double* d_v, const double* d_mass, double dt, double* d_ke,
                    void* stream) {
   if (!ctx || ctx->dd_n_loc <= 0 || !d_force || (d_v && !d_mass)) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
   return integ_denorm_scatter(ctx, ctx->perm, d_force, d_v, d_mass, dt, ctx->dd_n_loc, d_ke, (cudaStream_t)stream,
                               ctx->dd_n_own);
 }

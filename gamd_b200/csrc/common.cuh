@@ -107,6 +107,12 @@ struct gamd_ctx {
   int* tile_list[2] = {nullptr, nullptr};
   int* tile_count = nullptr;
   int sm_count = 148;
+  // one-time per-(device, kernel) opt-ins (cudaFuncSetAttribute is per device: tracked per context, not per process)
+  uint32_t attr_mask = 0;
+  // development switches read once at gamd_create (never on the launch path)
+  bool dbg_timeline = false;
+  int dd_reserve_sms = 0;
+  int mp_variant = 0;
 
   // optional per-stage CUDA-event timers (gamd_profile_enable / gamd_profile_read)
   struct StageProf {
@@ -142,6 +148,15 @@ void prof_mark(gamd_ctx* ctx, const char* stage, cudaStream_t st);   // call bef
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16 };
+
+// every stream entry point runs on the context's device, whatever device the calling thread had current
+#define GAMD_ENTER(ctx)                                                                  \
+  do {                                                                                   \
+    int _dev = -1;                                                                       \
+    if (cudaGetDevice(&_dev) != cudaSuccess || _dev != (ctx)->device) GAMD_CUDA(cudaSetDevice((ctx)->device)); \
+  } while (0)
+
 // ---- stage entry points implemented in the .cu files (host functions) ----
 int nbr_setup_params(gamd_ctx* ctx, int64_t n_atoms, int n_frames, const float box[3], float rc, int flags, NbrParams* p);
 int nbr_bin_f32(gamd_ctx* ctx, const float* d_pos, const NbrParams& p, cudaStream_t st);
@@ -161,7 +176,7 @@ int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64
 int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 int model_layer_edges(gamd_ctx* ctx, int l, cudaStream_t st, int which);
 int model_layer_nodes(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
-int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* feat, const int* orig_id,
+int model_forward(gamd_ctx* ctx, const float4* pos_feat, const float* feat, const int* orig_id,
                        int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st);
 
 int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);

@@ -349,11 +349,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_encode_tc(EncTcArgs a) {
 
 int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int atoms_per_frame,
                           const float box[3], cudaStream_t st) {
-  static bool attr_done = false;
   const size_t smem = sizeof(SmemEnc) + 1024;
-  if (!attr_done) {
+  if (!(ctx->attr_mask & GAMD_ATTR_ENC_TC)) {
     GAMD_CUDA(cudaFuncSetAttribute(k_edge_encode_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    ctx->attr_mask |= GAMD_ATTR_ENC_TC;
   }
   const ModelW& mw = ctx->mw;
   EncTcArgs a;

@@ -527,15 +527,14 @@ int set_smem(gamd_ctx* ctx, K kernel) {
 }  // namespace
 
 static int model_attrs(gamd_ctx* ctx) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!(ctx->attr_mask & GAMD_ATTR_FP32)) {
     int rc;
     if ((rc = set_smem(ctx, k_edge_encode))) return rc;
     if ((rc = set_smem(ctx, k_mp_edge))) return rc;
     if ((rc = set_smem(ctx, k_node_update<true, false>))) return rc;
     if ((rc = set_smem(ctx, k_node_update<false, false>))) return rc;
     if ((rc = set_smem(ctx, k_node_update<false, true>))) return rc;
-    attr_done = true;
+    ctx->attr_mask |= GAMD_ATTR_FP32;
   }
   return 0;
 }
@@ -646,7 +645,7 @@ int model_layer(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, c
   return model_layer_nodes(ctx, l, pos_feat, n_atoms, st);
 }
 
-int model_forward_fp32(gamd_ctx* ctx, const float4* pos_feat, const float* /*feat*/, const int* orig_id,
+int model_forward(gamd_ctx* ctx, const float4* pos_feat, const float* /*feat*/, const int* orig_id,
                        int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st) {
   int rc = model_begin(ctx, pos_feat, orig_id, n_atoms, atoms_per_frame, box, st);
   if (rc) return rc;

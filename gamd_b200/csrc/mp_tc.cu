@@ -564,11 +564,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
 }  // namespace
 
 int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which) {
-  static bool attr_done = false;
   const size_t smem = sizeof(SmemTC) + 1024;
-  if (!attr_done) {
+  if (!(ctx->attr_mask & GAMD_ATTR_MP_TC)) {
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    ctx->attr_mask |= GAMD_ATTR_MP_TC;
   }
   MpTcArgs a;
   a.w_img = ctx->d_wimg + (size_t)layer * 8 * WCHUNK;
@@ -586,9 +585,9 @@ int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which) {
   a.tile_list = which >= 0 ? ctx->tile_list[which] : nullptr;
   a.n_list = which >= 0 ? ctx->tile_count + which : nullptr;
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
-  a.dbg = (getenv("GAMD_TIMELINE") && layer == 1) ? reinterpret_cast<long long*>(ctx->e_emb + (size_t)ctx->cap_edges * 128) : nullptr;
+  a.dbg = (ctx->dbg_timeline && layer == 1) ? reinterpret_cast<long long*>(ctx->e_emb + (size_t)ctx->cap_edges * 128) : nullptr;
   // interior launch of a tile-split layer: optionally leave a few SMs to the halo exchange running beside it
-  static const int reserve = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
+  const int reserve = ctx->dd_reserve_sms;
   const int grid = which == 0 && reserve > 0 && reserve < ctx->sm_count ? ctx->sm_count - reserve : ctx->sm_count;
   k_mp_edge_tc<<<grid, THREADS, smem, st>>>(a);
   GAMD_LAUNCH_CHECK();

@@ -496,11 +496,10 @@ __global__ void k_agg_fixup(const int* __restrict__ row_ptr, const float* __rest
 
 // mode: 0 first (layer-0 prologue), 1 mid (after layer `layer`, prepares layer+1), 2 last (after the last layer)
 int node_update_tc_launch(gamd_ctx* ctx, int mode, int layer, const float4* pos_feat, int64_t n_atoms, cudaStream_t st) {
-  static bool attr_done = false;
   const size_t smem = sizeof(SmemNode) + 1024;
-  if (!attr_done) {
+  if (!(ctx->attr_mask & GAMD_ATTR_NODE_TC)) {
     GAMD_CUDA(cudaFuncSetAttribute(k_node_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    ctx->attr_mask |= GAMD_ATTR_NODE_TC;
   }
   const ModelW& mw = ctx->mw;
   if (mode != MODE_FIRST) {

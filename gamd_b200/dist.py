@@ -246,6 +246,10 @@ class SlabDomainMD:
         pos = self.x * 10.0
         if p.world > 1:
             to_l, to_r = p.halo_masks_centered(p.centered(pos[:, 0]))
+            if p.world == 2:
+                # left and right are the same rank: an atom within the halo of BOTH faces (slab narrower than two
+                # halos, e.g. the reference's own 27.27 A LJ box at rc = 7.5 A) must reach that peer only once
+                to_r = to_r & ~to_l
             table = _gather_stats(torch.stack([to_l.sum(), to_r.sum()]), p)      # the step's one host sync
             idx_l = _nonzero_n(to_l, int(table[p.rank, 0])).to(torch.int32)
             idx_r = _nonzero_n(to_r, int(table[p.rank, 1])).to(torch.int32)

@@ -83,9 +83,14 @@ class MDEngine:
                                 out=self.f)
         self.ctx.check_async_errors()
 
-    def step(self, n_steps, dt, ke=None):
+    def step(self, n_steps, dt, ke=None, check=True):
+        """n_steps device-resident MD steps.  ``check`` reads the device error flags afterwards (one stream
+        synchronisation per call): an edge-capacity overflow inside the run publishes an EMPTY edge list, so it must
+        surface as GAMD_ECAPACITY instead of silently integrating with zero-edge forces."""
         self.ctx.md_run(self.x, self.v, self.f, self.mass, self.box, self.cutoff, dt, n_steps, feat=self.feat,
                         n_frames=self.n_frames, ke=ke)
+        if check:
+            self.ctx.check_async_errors()
 
     def kinetic_energy(self):
         return float(0.5 * (self.mass[:, None] * self.v * self.v).sum().item())
@@ -164,8 +169,10 @@ class TIP4PEngine:
         c.check_async_errors()
         self._sync_out()
 
-    def step(self, n_steps, dt):
-        self.eng.step(n_steps, dt)
+    def step(self, n_steps, dt, check=None):
+        # callers that advance one step per call (bench) would pay a host sync per step: check every 64th call
+        self._calls = getattr(self, "_calls", 0) + 1
+        self.eng.step(n_steps, dt, check=(n_steps > 1 or self._calls % 64 == 0) if check is None else check)
         self._sync_out()
 
     def close(self):

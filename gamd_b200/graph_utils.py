@@ -67,7 +67,11 @@ class NeighborSearcher(object):
 def graph_network_nbr_fn(displacement_fn, cutoff, N):
     """Returns ``fn(pos, neigh_idx) -> mask[N, K]`` (code/graph_utils.py:47-63).  ``neigh_idx`` comes from
     ``NeighborSearcher`` above, which already holds exactly the pairs passing ``dr2 < cutoff**2``, so the
-    mask is the padding mask; the exact fp32 predicate itself lives in the CUDA sweep kernel."""
+    mask is the padding mask; the exact fp32 predicate itself lives in the CUDA sweep kernel.
+
+    The mask is therefore valid only for the positions the list was BUILT from (``update_neighbor_lst`` rebuilds
+    on every call, so the reference's call order - update, then mask with the same positions,
+    train_network_lj.py:194-197 - always satisfies that); ``pos`` is accepted for signature compatibility."""
 
     def nbrlst_to_edge_mask(pos, neigh_idx):
         return neigh_idx != N

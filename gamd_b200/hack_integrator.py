@@ -185,7 +185,9 @@ class _NHCMixin:
             g[f"xi{i}"] = 0.0
             g[f"vxi{i}"] = 0.0
             g[f"G{i}"] = -frequency ** 2
-            g[f"Q{i}"] = (ndf * q if i == 0 else q) if ndf is not None else 0.0
+            # Q1..Q{M-1} = Q always (the reference sets them inside the step program, hack_integrator.py:283-287);
+            # Q0 = ndf * Q is fixed in propagateNHC when the system (ndf) is only known at bind time
+            g[f"Q{i}"] = q if i else (ndf * q if ndf is not None else 0.0)
 
     def propagateNHC(self):
         """hack_integrator.py:289-316 / :454-481: chain scalars on the host, one KE reduction and one

@@ -32,16 +32,18 @@ class FakeBackend:
     the complete neighbourhood) - computed with the oracle predicate on the local atoms, global box."""
     row_width = 4
 
-    def __init__(self):
+    def __init__(self, box=BOX):
         self.n_layers = N_LAYERS
         self.log = []
+        self.box = box
 
     def begin(self, pos_local, n_own, feat_local):
         self.pos, self.n_own, self.gid = pos_local.numpy(), n_own, feat_local.numpy().round().astype(np.int64)
+        assert len(np.unique(self.gid)) == len(self.gid), "an atom reached this rank twice (duplicated halo row)"
         self.rows = np.full((len(self.pos), 4), -1.0, np.float32)
         self.rows[:, 0], self.rows[:, 1] = self.gid, 0            # layer-0 input is position independent
-        p = onb.wrap_f32(self.pos.astype(np.float32), BOX)
-        e = onb.edges_bruteforce(p, BOX, RC)
+        p = onb.wrap_f32(self.pos.astype(np.float32), self.box)
+        e = onb.edges_bruteforce(p, self.box, RC)
         self.edges = e[:, e[0] < n_own]
 
     def layer(self, l):
@@ -63,17 +65,17 @@ class FakeBackend:
             v_own += (dt / 2) * f_own / mass_own[:, None]
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, BOX=BOX):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         rng = np.random.Generator(np.random.PCG64(5))
-        n = 600
+        n = 600 if BOX >= 40.0 else 258
         x = rng.uniform(0, BOX, (n, 3)) / 10.0 - 1.0             # nm, partly outside the box
         v = rng.standard_normal((n, 3)) * 0.5
         m = np.full(n, 39.9)
         plan = SlabPlan(BOX, RC, world, rank)
-        md = SlabDomainMD.scatter_global(FakeBackend(), plan, x, v, m, "cpu", feat_all=np.arange(n, dtype=np.float32))
+        md = SlabDomainMD.scatter_global(FakeBackend(BOX), plan, x, v, m, "cpu", feat_all=np.arange(n, dtype=np.float32))
         counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(counts, torch.tensor([md.x.shape[0]]))
         assert sum(int(c) for c in counts) == n
@@ -107,6 +109,19 @@ def test_slab_decomposition_gloo(world):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert len(ret) == world and len(set(round(v, 9) for v in ret.values())) == 1
+
+
+def test_two_ranks_narrow_box_sends_each_halo_atom_once():
+    """world 2, the reference's own LJ box (27.27 A, rc 7.5 A): slab width 13.6 A < 2 halos, so an atom near the slab
+    centre is within the halo of both faces - and both faces border the SAME peer.  It must arrive there once."""
+    plan = SlabPlan(27.27, RC, 2, 0)
+    both = [a and b for a, b in zip(*[m.tolist() for m in plan.halo_masks_centered(torch.linspace(-6.8, 6.8, 200,
+                                                                                                dtype=torch.float64))])]
+    assert any(both)                       # the geometry really has doubly-selected atoms
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret, 27.27), nprocs=2, join=True)
+    assert len(ret) == 2 and len(set(round(v, 9) for v in ret.values())) == 1
 
 
 def test_single_rank_plan_has_no_halo():
