@@ -33,6 +33,24 @@ class ModelDesc(ctypes.Structure):
                 ("precision", c_int32)]
 
 
+NHC_MAX = 16
+THERMO_NONE, THERMO_NHC, THERMO_LANGEVIN = 0, 1, 2
+
+
+class NhcState(ctypes.Structure):
+    """host mirror of ``gamd_nhc_state`` (the Nose-Hoover chain globals of code/hack_integrator.py:249-261)."""
+    _fields_ = [("M", c_int32), ("n_c", c_int32), ("n_ys", c_int32), ("pad_", c_int32),
+                ("kT", c_double), ("ndf", c_double), ("Qbase", c_double),
+                ("xi", c_double * NHC_MAX), ("vxi", c_double * NHC_MAX), ("G", c_double * NHC_MAX), ("Q", c_double * NHC_MAX),
+                ("scale", c_double), ("ke2_in", c_double), ("ke2", c_double), ("bathKE", c_double), ("bathPE", c_double)]
+
+
+class MdOptions(ctypes.Structure):
+    _fields_ = [("thermostat", c_int32), ("chain_length", c_int32), ("num_mts", c_int32), ("num_ys", c_int32),
+                ("kT", c_double), ("frequency", c_double), ("ndf", c_double), ("friction", c_double),
+                ("seed", ctypes.c_uint64), ("rigid_water", c_int32), ("pad_", c_int32), ("d_oh", c_double), ("d_hh", c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/gamd_b200.h declares
 SIGNATURES = {
     "gamd_create": (c_int32, [c_int32, POINTER(ModelDesc), POINTER(c_void_p)]),
@@ -59,6 +77,18 @@ SIGNATURES = {
                               c_float, c_void_p, c_double, c_int32, c_void_p, c_void_p]),
     "gamd_md_step_host": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                     POINTER(c_double), c_float, c_void_p, c_double]),
+    "gamd_md_configure": (c_int32, [c_void_p, POINTER(MdOptions)]),
+    "gamd_nhc_init_state": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_double, c_double, c_void_p]),
+    "gamd_nhc_propagate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_int32, c_void_p]),
+    "gamd_nhc_get_state": (c_int32, [c_void_p, c_void_p, POINTER(NhcState), c_void_p]),
+    "gamd_nhc_set_state": (c_int32, [c_void_p, c_void_p, POINTER(NhcState), c_void_p]),
+    "gamd_langevin_first_half": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
+                                           c_double, c_void_p, c_void_p]),
+    "gamd_andersen_collide": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p,
+                                        c_void_p]),
+    "gamd_settle_positions": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
+                                        c_double, c_void_p]),
+    "gamd_settle_velocities": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "gamd_tip4p_strip": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "gamd_tip4p_unstrip": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_void_p]),
     "gamd_dd_begin": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_double), c_float, c_void_p, c_void_p]),
@@ -236,6 +266,49 @@ class Context:
     def md_step_host(self, x, v, f, mass, box, cutoff, dt, feat=None, n_frames=1):
         self._check(self.lib.gamd_md_step_host(self._h, _ptr(x), _ptr(v), _ptr(f), _ptr(mass), x.shape[0], n_frames,
                                                _box3(box), float(cutoff), _ptr(feat), float(dt)))
+
+    # ---- thermostats / constraints ----
+    def md_configure(self, thermostat=THERMO_NONE, kT=0.0, chain_length=5, num_mts=5, num_ys=5, frequency=50.0,
+                     ndf=0.0, friction=1.0, seed=0, rigid_water=False, d_oh=0.0, d_hh=0.0):
+        """program of the device-resident loop (``md_run``): NVE / Nose-Hoover chain / Langevin, rigid water or not."""
+        opt = MdOptions(int(thermostat), int(chain_length), int(num_mts), int(num_ys), float(kT), float(frequency),
+                        float(ndf), float(friction), int(seed), int(bool(rigid_water)), 0, float(d_oh), float(d_hh))
+        self._check(self.lib.gamd_md_configure(self._h, ctypes.byref(opt)))
+
+    def nhc_new_state(self, chain_length, num_mts, num_ys, kT, frequency, ndf):
+        """a caller-owned device-resident chain (one per Hack*Integrator object)."""
+        import torch
+        st = torch.zeros(ctypes.sizeof(NhcState), dtype=torch.uint8, device=torch.device("cuda", self.device))
+        self._check(self.lib.gamd_nhc_init_state(self._h, _ptr(st), int(chain_length), int(num_mts), int(num_ys),
+                                                 float(kT), float(frequency), float(ndf), _stream()))
+        return st
+
+    def nhc_propagate(self, v, mass, dt, state=None, bath=False):
+        self._check(self.lib.gamd_nhc_propagate(self._h, _ptr(state), _ptr(v), _ptr(mass), v.shape[0], float(dt),
+                                                int(bool(bath)), _stream()))
+
+    def nhc_get_state(self, state=None):
+        h = NhcState()
+        self._check(self.lib.gamd_nhc_get_state(self._h, _ptr(state), ctypes.byref(h), _stream()))
+        return h
+
+    def nhc_set_state(self, h, state=None):
+        self._check(self.lib.gamd_nhc_set_state(self._h, _ptr(state), ctypes.byref(h), _stream()))
+
+    def langevin_first_half(self, x, v, f, mass, dt, kT, friction, gaussian=None):
+        self._check(self.lib.gamd_langevin_first_half(self._h, _ptr(x), _ptr(v), _ptr(f), _ptr(mass), x.shape[0],
+                                                      float(dt), float(kT), float(friction), _ptr(gaussian), _stream()))
+
+    def andersen_collide(self, v, mass, kT, p_collision, uniform=None, gaussian=None):
+        self._check(self.lib.gamd_andersen_collide(self._h, _ptr(v), _ptr(mass), v.shape[0], float(kT),
+                                                   float(p_collision), _ptr(uniform), _ptr(gaussian), _stream()))
+
+    def settle_positions(self, x0, x, mass, v=None, dt_corr=0.0, d_oh=0.0, d_hh=0.0):
+        self._check(self.lib.gamd_settle_positions(self._h, _ptr(x0), _ptr(x), _ptr(v), _ptr(mass), x.shape[0] // 3,
+                                                   float(dt_corr), float(d_oh), float(d_hh), _stream()))
+
+    def settle_velocities(self, x, v, mass):
+        self._check(self.lib.gamd_settle_velocities(self._h, _ptr(x), _ptr(v), _ptr(mass), x.shape[0] // 3, _stream()))
 
     def tip4p_strip(self, x4, x3):
         self._check(self.lib.gamd_tip4p_strip(self._h, _ptr(x4), _ptr(x3), x4.shape[0] // 4, _stream()))

@@ -249,9 +249,12 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   ctx->use_graphs = getenv("GAMD_NO_GRAPH") == nullptr;
   ctx->dbg_timeline = getenv("GAMD_TIMELINE") != nullptr;
   ctx->dd_reserve_sms = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
-  ctx->mp_variant = getenv("GAMD_MP_VARIANT") ? atoi(getenv("GAMD_MP_VARIANT")) : 0;
+  // message-passing edge kernel: 6 = CTA pairs (cta_group::2), resident weights, three tiles in flight (default);
+  // 5 = the same with a commit wait between GEMMs; 3 / 4 = three tiles, single CTA; 0 = the round-1 two-tile kernel
+  ctx->mp_variant = getenv("GAMD_MP_VARIANT") ? atoi(getenv("GAMD_MP_VARIANT")) : 6;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (ctx->sm_count < 2 && ctx->mp_variant >= 5) ctx->mp_variant = 0;
   *out = ctx;
   return 0;
 }
@@ -262,11 +265,13 @@ int gamd_destroy(gamd_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->d_wblob) cudaFree(ctx->d_wblob);
   if (ctx->d_wimg) cudaFree(ctx->d_wimg);
+  if (ctx->d_wimg2) cudaFree(ctx->d_wimg2);
   if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
   if (ctx->d_wimg_enc) cudaFree(ctx->d_wimg_enc);
   if (ctx->d_tc_bias_enc) cudaFree(ctx->d_tc_bias_enc);
   if (ctx->d_wimg_node) cudaFree(ctx->d_wimg_node);
   if (ctx->d_bond) cudaFree(ctx->d_bond);
+  if (ctx->d_nhc) cudaFree(ctx->d_nhc);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   if (ctx->graph_stream) cudaStreamDestroy(ctx->graph_stream);
@@ -505,6 +510,33 @@ int gamd_finalize_weights(gamd_ctx* ctx) {
           }
         for (int n = 0; n < 128; n++) tb[(size_t)(l * 4 + s) * 128 + n] = b[n];
       }
+    // the same matrices for the CTA-pair kernel (tcgen05 cta_group::2): CTA h of a pair holds rows n = 64 h .. 64 h + 63
+    // of B, so that a CTA's 128 KB (4 stages x [hi | lo] x 16 KB) are contiguous: [layer][half][stage][part]
+    {
+      const size_t part = 16384;
+      std::vector<uint8_t> img2((size_t)d.conv_layer * 2 * 4 * 2 * part, 0);
+      for (int l = 0; l < d.conv_layer; l++)
+        for (int s = 0; s < 4; s++) {
+          const std::vector<float>& w = ctx->host_w["graph_conv.conv." + std::to_string(l) + "." + names[s] + ".weight"];
+          for (int n = 0; n < 128; n++) {
+            const int half = n >> 6, nl = n & 63;
+            uint8_t* hi = img2.data() + ((((size_t)l * 2 + half) * 4 + s) * 2 + 0) * part;
+            uint8_t* lo = hi + part;
+            for (int k = 0; k < 128; k++) {
+              float x = w[(size_t)n * 128 + k];
+              uint16_t h = bf16_rn(x);
+              uint16_t lw = bf16_rn(x - bf16_f(h));
+              size_t off = (size_t)(k >> 6) * 8192 + (size_t)nl * 128 + ((((k & 63) >> 3) ^ (nl & 7)) << 4) + ((k & 7) << 1);
+              memcpy(hi + off, &h, 2);
+              memcpy(lo + off, &lw, 2);
+            }
+          }
+        }
+      if (ctx->d_wimg2) cudaFree(ctx->d_wimg2);
+      ctx->d_wimg2 = nullptr;
+      GAMD_CUDA(cudaMalloc(&ctx->d_wimg2, img2.size()));
+      GAMD_CUDA(cudaMemcpy(ctx->d_wimg2, img2.data(), img2.size(), cudaMemcpyHostToDevice));
+    }
     if (ctx->d_wimg) cudaFree(ctx->d_wimg);
     if (ctx->d_tc_bias) cudaFree(ctx->d_tc_bias);
     ctx->d_wimg = nullptr;
@@ -717,17 +749,64 @@ int gamd_md_run(gamd_ctx* ctx, double* d_x, double* d_v, double* d_f, const doub
   if (n_steps == 0) return 0;
   if (d_ke) GAMD_CUDA(cudaMemsetAsync(d_ke, 0, sizeof(double) * n_steps, st));
   GAMD_CUDA(cudaMemsetAsync(ctx->d_stepctr, 0, sizeof(int), st));
-  auto one_step = [&](cudaStream_t s_) -> int {
+  // the step program: plain velocity Verlet, or the thermostat / constraint programs chosen by gamd_md_configure
+  const gamd_md_options& md = ctx->md;
+  const bool nhc = md.thermostat == GAMD_THERMO_NHC && md.chain_length > 0;
+  const bool langevin = md.thermostat == GAMD_THERMO_LANGEVIN;
+  const bool rigid = md.rigid_water != 0;
+  const double d_oh = md.d_oh > 0 ? md.d_oh : 0.09572, d_hh = md.d_hh > 0 ? md.d_hh : 0.15139006545273223;
+  if (rigid && (n_atoms % 3 || n_frames < 1)) {
+    ctx->err = "rigid_water needs [O,H,H] triplets";
+    return GAMD_EINVAL;
+  }
+  if (langevin && rigid) {
+    ctx->err = "the device-resident loop runs Langevin without constraints; rigid water: use Nose-Hoover or NVE";
+    return GAMD_EUNSUPPORTED;
+  }
+  if ((nhc || langevin) && !ctx->d_nhc) {
+    ctx->err = "gamd_md_configure was not called";
+    return GAMD_ESTATE;
+  }
+  const int64_t n_mol = n_atoms / 3;
+  if (nhc) {
+    // KE2 = sum m v^2 of the caller's velocities for the first chain propagation; afterwards the sum is carried
+    // analytically (scale^2 * KE2) or comes out of the kick kernel's reduction
+    if ((rc = thermo_ke2(ctx, d_v, d_mass, n_atoms, ctx->d_ke2_acc, st))) return rc;
+  }
+  // fresh: the first chain of this call reads the reduction above, later ones the cached post-scaling sum
+  auto one_step = [&](cudaStream_t s_, bool fresh) -> int {
     int r;
-    if ((r = integ_first_half(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, s_))) return r;
+    if (nhc) {                                                    // propagateNHC (hack_integrator.py:271)
+      if (fresh) r = thermo_chain(ctx, ctx->d_nhc, ctx->d_ke2_acc, dt, 0, nullptr, nullptr, s_);
+      else r = thermo_chain_cached(ctx, ctx->d_nhc, dt, 0, s_);
+      if (r) return r;
+    }
+    prof_mark(ctx, "integrate", s_);
+    if (rigid) r = thermo_vv_first_rigid(ctx, d_x, d_v, d_f, d_mass, n_mol, dt, nhc, d_oh, d_hh, s_);
+    else if (nhc) r = thermo_vv_first_scaled(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, s_);
+    else if (langevin) r = thermo_langevin_first(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, md.kT, md.friction, nullptr, s_);
+    else r = integ_first_half(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, s_);
+    prof_mark(ctx, "integrate", s_);
+    if (r) return r;
     // forces at x*10 Angstrom (test_nosehoover.py:112: value_in_unit(angstrom))
     if ((r = positions_to_forces(ctx, d_x, 10.0, n_atoms, n_frames, h_box, cutoff, d_feat, s_))) return r;
-    if ((r = integ_denorm_scatter(ctx, ctx->perm, d_f, d_v, d_mass, dt, n_atoms, d_ke, s_, -1, ctx->d_stepctr))) return r;
+    // second half: kick (+ constrain velocities) (+ propagateNHC, bath energies); kinetic energy of the final velocities
+    double* ke_kick = (rigid || nhc) ? nullptr : d_ke;
+    double* acc_kick = (nhc && !rigid) ? ctx->d_ke2_acc : nullptr;
+    if ((r = integ_denorm_scatter(ctx, ctx->perm, d_f, d_v, d_mass, dt, n_atoms, ke_kick, s_, -1, ctx->d_stepctr, acc_kick)))
+      return r;
+    if (rigid && (r = thermo_settle_vel(ctx, d_x, d_v, d_mass, n_mol, nhc ? ctx->d_ke2_acc : nullptr, nhc ? nullptr : d_ke,
+                                        ctx->d_stepctr, s_)))
+      return r;
+    if (nhc) {
+      if ((r = thermo_chain(ctx, ctx->d_nhc, ctx->d_ke2_acc, dt, 1, d_ke, ctx->d_stepctr, s_))) return r;
+      if ((r = thermo_scale_v(ctx, ctx->d_nhc, d_v, n_atoms, s_))) return r;
+    }
     return d_ke ? integ_inc_counter(ctx, ctx->d_stepctr, s_) : 0;
   };
   // the first step always runs eagerly (it also sets the one-time kernel attributes)
   const int64_t l0 = ctx->launches;
-  if ((rc = one_step(st))) return rc;
+  if ((rc = one_step(st, true))) return rc;
   ctx->launches_last_step = ctx->launches - l0;
   int done = 1;
   // launch-bound systems: capture one step into a CUDA graph and replay it (every grid is shape-static: tile
@@ -742,6 +821,7 @@ int gamd_md_run(gamd_ctx* ctx, double* d_x, double* d_v, double* d_f, const doub
     for (int d = 0; d < 3; d++) { memcpy(&bits, &h_box[d], 8); mix(bits); }
     memcpy(&bits, &dt, 8); mix(bits);
     uint32_t cb; memcpy(&cb, &cutoff, 4); mix(cb);
+    mix(ctx->md_generation);
     // (scaler, weights, bonds: gamd_set_scaler / gamd_finalize_weights / gamd_set_bonds reset graph_key themselves)
     if (!ctx->graph_stream) {
       GAMD_CUDA(cudaStreamCreateWithFlags(&ctx->graph_stream, cudaStreamNonBlocking));
@@ -755,7 +835,7 @@ int gamd_md_run(gamd_ctx* ctx, double* d_x, double* d_v, double* d_f, const doub
       cudaGraph_t graph = nullptr;
       const int64_t launches0 = ctx->launches;
       GAMD_CUDA(cudaStreamBeginCapture(ctx->graph_stream, cudaStreamCaptureModeThreadLocal));
-      rc = one_step(ctx->graph_stream);
+      rc = one_step(ctx->graph_stream, false);
       cudaError_t ce = cudaStreamEndCapture(ctx->graph_stream, &graph);
       ctx->launches = launches0;   // captured, not launched
       if (rc) {
@@ -790,7 +870,7 @@ int gamd_md_run(gamd_ctx* ctx, double* d_x, double* d_v, double* d_f, const doub
     GAMD_CUDA(cudaStreamWaitEvent(st, ctx->graph_ev_out, 0));
   }
   for (; done < n_steps; done++)
-    if ((rc = one_step(st))) return rc;
+    if ((rc = one_step(st, false))) return rc;
   return 0;
 }
 
@@ -818,6 +898,124 @@ int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, cons
   GAMD_CUDA(cudaMemcpyAsync(h_v, ctx->stage_b, b3, cudaMemcpyDeviceToHost, st));
   GAMD_CUDA(cudaMemcpyAsync(h_f, ctx->stage_c, b3, cudaMemcpyDeviceToHost, st));
   return gamd_check_async_errors(ctx, st);
+}
+
+int gamd_md_configure(gamd_ctx* ctx, const gamd_md_options* opt) {
+  if (!ctx || !opt) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  if (opt->thermostat < GAMD_THERMO_NONE || opt->thermostat > GAMD_THERMO_LANGEVIN) return GAMD_EINVAL;
+  int rc = thermo_alloc(ctx);
+  if (rc) return rc;
+  ctx->md = *opt;
+  ctx->md_generation++;
+  ctx->graph_key = 0;
+  GAMD_CUDA(cudaMemsetAsync(ctx->d_rng_ctr, 0, sizeof(unsigned long long), 0));
+  if (opt->thermostat == GAMD_THERMO_NHC) {
+    if (opt->ndf <= 0) {
+      ctx->err = "Nose-Hoover needs the number of degrees of freedom (3 N - constraints [- 3])";
+      return GAMD_EINVAL;
+    }
+    return gamd_nhc_init_state(ctx, nullptr, opt->chain_length, opt->num_mts, opt->num_ys, opt->kT, opt->frequency, opt->ndf, 0);
+  }
+  return 0;
+}
+
+int gamd_nhc_init_state(gamd_ctx* ctx, gamd_nhc_state* d_state, int32_t chain_length, int32_t num_mts, int32_t num_ys,
+                        double kT, double frequency, double ndf, void* stream) {
+  if (!ctx) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  if (chain_length < 0 || chain_length > GAMD_NHC_MAX) {
+    ctx->err = "Nose-Hoover chain length must be in 0.." + std::to_string(GAMD_NHC_MAX);
+    return GAMD_EINVAL;
+  }
+  if (num_ys != 1 && num_ys != 3 && num_ys != 5) {
+    ctx->err = "Invalid Yoshida-Suzuki value. Allowed values are: 1,3,5";
+    return GAMD_EINVAL;
+  }
+  if (num_mts < 1 || !(frequency > 0) || !(kT > 0)) return GAMD_EINVAL;
+  if (!d_state) {
+    int rc = thermo_alloc(ctx);
+    if (rc) return rc;
+    d_state = ctx->d_nhc;
+  }
+  gamd_nhc_state h{};
+  h.M = chain_length; h.n_c = num_mts; h.n_ys = num_ys;
+  h.kT = kT; h.ndf = ndf; h.Qbase = kT / (frequency * frequency);
+  for (int i = 0; i < chain_length; i++) {
+    h.G[i] = -frequency * frequency;                                  // hack_integrator.py:257
+    h.Q[i] = i == 0 ? ndf * h.Qbase : h.Qbase;
+  }
+  h.scale = 1.0;
+  GAMD_CUDA(cudaMemcpyAsync(d_state, &h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  GAMD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));              // `h` lives on this stack frame
+  return 0;
+}
+
+int gamd_nhc_propagate(gamd_ctx* ctx, gamd_nhc_state* d_state, double* d_v, const double* d_mass, int64_t n_atoms,
+                       double dt, int32_t bath, void* stream) {
+  if (!ctx || !d_v || !d_mass || n_atoms <= 0) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  int rc = thermo_alloc(ctx);
+  if (rc) return rc;
+  if (!d_state) d_state = ctx->d_nhc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = thermo_ke2(ctx, d_v, d_mass, n_atoms, ctx->d_ke2_acc, st))) return rc;
+  if ((rc = thermo_chain(ctx, d_state, ctx->d_ke2_acc, dt, bath, nullptr, nullptr, st))) return rc;
+  return thermo_scale_v(ctx, d_state, d_v, n_atoms, st);
+}
+
+int gamd_nhc_get_state(gamd_ctx* ctx, const gamd_nhc_state* d_state, gamd_nhc_state* h_out, void* stream) {
+  if (!ctx || !h_out) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  if (!d_state) d_state = ctx->d_nhc;
+  if (!d_state) return GAMD_ESTATE;
+  GAMD_CUDA(cudaMemcpyAsync(h_out, d_state, sizeof(gamd_nhc_state), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GAMD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int gamd_nhc_set_state(gamd_ctx* ctx, gamd_nhc_state* d_state, const gamd_nhc_state* h_in, void* stream) {
+  if (!ctx || !h_in) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  if (!d_state) d_state = ctx->d_nhc;
+  if (!d_state) return GAMD_ESTATE;
+  GAMD_CUDA(cudaMemcpyAsync(d_state, h_in, sizeof(gamd_nhc_state), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  GAMD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int gamd_langevin_first_half(gamd_ctx* ctx, double* d_x, double* d_v, const double* d_f, const double* d_mass,
+                             int64_t n_atoms, double dt, double kT, double friction, const double* d_gaussian,
+                             void* stream) {
+  if (!ctx || !d_x || !d_v || !d_f || !d_mass || n_atoms <= 0) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  int rc = thermo_alloc(ctx);
+  if (rc) return rc;
+  return thermo_langevin_first(ctx, d_x, d_v, d_f, d_mass, n_atoms, dt, kT, friction, d_gaussian, (cudaStream_t)stream);
+}
+
+int gamd_andersen_collide(gamd_ctx* ctx, double* d_v, const double* d_mass, int64_t n_atoms, double kT,
+                          double p_collision, const double* d_uniform, const double* d_gaussian, void* stream) {
+  if (!ctx || !d_v || !d_mass || n_atoms <= 0 || ((d_uniform == nullptr) != (d_gaussian == nullptr))) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  int rc = thermo_alloc(ctx);
+  if (rc) return rc;
+  return thermo_andersen(ctx, d_v, d_mass, n_atoms, kT, p_collision, d_uniform, d_gaussian, (cudaStream_t)stream);
+}
+
+int gamd_settle_positions(gamd_ctx* ctx, const double* d_x0, double* d_x, double* d_v, const double* d_mass,
+                          int64_t n_mol, double dt_corr, double d_oh, double d_hh, void* stream) {
+  if (!ctx || !d_x0 || !d_x || !d_mass || n_mol <= 0 || (d_v && !(dt_corr > 0))) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  return thermo_settle_pos(ctx, d_x0, d_x, d_v, d_mass, n_mol, dt_corr, d_oh > 0 ? d_oh : 0.09572,
+                           d_hh > 0 ? d_hh : 0.15139006545273223, (cudaStream_t)stream);
+}
+
+int gamd_settle_velocities(gamd_ctx* ctx, const double* d_x, double* d_v, const double* d_mass, int64_t n_mol,
+                           void* stream) {
+  if (!ctx || !d_x || !d_v || !d_mass || n_mol <= 0) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  return thermo_settle_vel(ctx, d_x, d_v, d_mass, n_mol, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int gamd_tip4p_strip(gamd_ctx* ctx, const double* d_x4, double* d_x3, int64_t n_mol, void* stream) {

@@ -58,6 +58,7 @@ struct gamd_ctx {
   double scaler_mean = 0.0, scaler_var = 1.0;
   uint8_t* d_wimg = nullptr;      // tcgen05 weight images: [layer][4 stages][hi,lo][32 KB] SW128 K-major bf16
   float* d_tc_bias = nullptr;     // [layer][4][128]
+  uint8_t* d_wimg2 = nullptr;     // CTA-pair images: [layer][2 halves of the 128 rows of B][4 stages][hi,lo][16 KB]
   uint8_t* d_wimg_enc = nullptr;  // edge encoder images: enc0 hi|lo (16 KB each, K=64), enc2 hi|lo, enc4 hi|lo (32 KB each)
   float* d_tc_bias_enc = nullptr; // [3][128]
   uint8_t* d_wimg_node = nullptr; // node matrices: [layer][pedge, phi, src, dst, pdst, dec0][hi|lo][32 KB]
@@ -114,6 +115,13 @@ struct gamd_ctx {
   int dd_reserve_sms = 0;
   int mp_variant = 0;
 
+  // thermostat / constraints of the device-resident loop (gamd_md_configure)
+  gamd_md_options md{};
+  uint64_t md_generation = 0;
+  gamd_nhc_state* d_nhc = nullptr;            // chain state + [ke2 accumulator][variate step counter] behind it
+  double* d_ke2_acc = nullptr;
+  unsigned long long* d_rng_ctr = nullptr;
+
   // optional per-stage CUDA-event timers (gamd_profile_enable / gamd_profile_read)
   struct StageProf {
     std::vector<cudaEvent_t> ev;   // begin/end pairs
@@ -148,7 +156,7 @@ void prof_mark(gamd_ctx* ctx, const char* stage, cudaStream_t st);   // call bef
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16 };
+enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16, GAMD_ATTR_MP_TC2 = 32 };
 
 // every stream entry point runs on the context's device, whatever device the calling thread had current
 #define GAMD_ENTER(ctx)                                                                  \
@@ -168,6 +176,8 @@ int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cu
 
 // which: -1 every tile; 0 / 1 only the interior / boundary tiles of the domain-decomposition split (ctx->tile_list)
 int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which = -1);
+int mp_edge_tc3_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war);
+int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war);
 int node_update_tc_launch(gamd_ctx* ctx, int mode, int layer, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int atoms_per_frame,
                           const float box[3], cudaStream_t st);
@@ -181,8 +191,26 @@ int model_forward(gamd_ctx* ctx, const float4* pos_feat, const float* feat, cons
 
 int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
 int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
-int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt, int64_t n, double* ke_out, cudaStream_t st, int64_t n_own = -1, const int* ke_slot = nullptr);
+int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt, int64_t n, double* ke_out, cudaStream_t st, int64_t n_own = -1, const int* ke_slot = nullptr, double* ke2_acc = nullptr);
 int integ_inc_counter(gamd_ctx* ctx, int* counter, cudaStream_t st);
 int integ_tip4p_strip(gamd_ctx* ctx, const double* x4, double* x3, int64_t n_mol, cudaStream_t st);
 int integ_tip4p_unstrip(gamd_ctx* ctx, const double* a3, double* a4, int64_t n_mol, double wo, double wh, int place_m, cudaStream_t st);
+int thermo_alloc(gamd_ctx* ctx);
+int thermo_ke2(gamd_ctx* ctx, const double* v, const double* mass, int64_t n, double* acc, cudaStream_t st);
+int thermo_chain(gamd_ctx* ctx, gamd_nhc_state* d_state, double* ke2_acc, double dt, int bath, double* ke_out,
+                 const int* ke_slot, cudaStream_t st);
+int thermo_chain_cached(gamd_ctx* ctx, gamd_nhc_state* d_state, double dt, int bath, cudaStream_t st);
+int thermo_scale_v(gamd_ctx* ctx, const gamd_nhc_state* d_state, double* v, int64_t n, cudaStream_t st);
+int thermo_vv_first_scaled(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt,
+                           cudaStream_t st);
+int thermo_langevin_first(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt,
+                          double kT, double friction, const double* gaussian, cudaStream_t st);
+int thermo_andersen(gamd_ctx* ctx, double* v, const double* mass, int64_t n, double kT, double p_coll,
+                    const double* uniform, const double* gaussian, cudaStream_t st);
+int thermo_settle_pos(gamd_ctx* ctx, const double* x0, double* x, double* v, const double* mass, int64_t n_mol,
+                      double dt_corr, double d_oh, double d_hh, cudaStream_t st);
+int thermo_vv_first_rigid(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n_mol,
+                          double dt, bool scaled, double d_oh, double d_hh, cudaStream_t st);
+int thermo_settle_vel(gamd_ctx* ctx, const double* x, double* v, const double* mass, int64_t n_mol, double* ke2_acc,
+                      double* ke_out, const int* ke_slot, cudaStream_t st);
 int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st);

@@ -35,7 +35,7 @@ __global__ void k_vv_second(double* __restrict__ v, const double* __restrict__ f
 __global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __restrict__ perm, int64_t n, int64_t n_own,
                                  double sigma, double mean, double* __restrict__ f, double* __restrict__ v,
                                  const double* __restrict__ mass, double dt, double* __restrict__ ke,
-                                 const int* __restrict__ ke_slot) {
+                                 const int* __restrict__ ke_slot, double* __restrict__ ke2_acc) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double local = 0.0;
   int64_t i = s < n ? (perm ? perm[s] : s) : n_own;
@@ -52,7 +52,7 @@ __global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __re
       }
     }
   }
-  if (ke) {
+  if (ke || ke2_acc) {
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     __shared__ double sw[8];
@@ -61,7 +61,8 @@ __global__ void k_denorm_scatter(const float* __restrict__ pred, const int* __re
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sw[w];
-      atomicAdd(ke + (ke_slot ? *ke_slot : 0), t);
+      if (ke) atomicAdd(ke + (ke_slot ? *ke_slot : 0), t);
+      if (ke2_acc) atomicAdd(ke2_acc, 2.0 * t);      // sum m v^2 for the thermostat chain that follows the kick
     }
   }
 }
@@ -83,13 +84,13 @@ int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* m
 }
 
 int integ_denorm_scatter(gamd_ctx* ctx, const int* perm, double* f_out, double* v, const double* mass, double dt,
-                         int64_t n, double* ke_out, cudaStream_t st, int64_t n_own, const int* ke_slot) {
+                         int64_t n, double* ke_out, cudaStream_t st, int64_t n_own, const int* ke_slot, double* ke2_acc) {
   if (n_own < 0) n_own = n;
   // ke_slot != nullptr: ke_out is a per-step trace zeroed by the caller, *ke_slot selects the entry (CUDA-graph replay)
   if (ke_out && !ke_slot) GAMD_CUDA(cudaMemsetAsync(ke_out, 0, sizeof(double), st));
   prof_mark(ctx, "integrate", st);
   k_denorm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(ctx->pred, perm, n, n_own, sqrt(ctx->scaler_var), ctx->scaler_mean,
-                                                     f_out, v, mass, dt, ke_out, ke_slot);
+                                                     f_out, v, mass, dt, ke_out, ke_slot, ke2_acc);
   GAMD_LAUNCH_CHECK();
   prof_mark(ctx, "integrate", st);
   return 0;

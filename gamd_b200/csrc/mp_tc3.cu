@@ -11,9 +11,15 @@
 //   precision "bf16x3": x = hi + lo (two bf16), D = Ahi*Bhi + Alo*Bhi + Ahi*Blo  -> fp32-grade result
 //   precision "bf16"  : single pass on the hi parts
 //
-// CTA = 18 warps: 16 epilogue warps (thread = edge row; two 128-edge tiles in flight, 8 warps each = 4 TMEM
-// lane quadrants x 2 column halves; the two tiles ping-pong on the tensor core and share every weight
-// load), 1 MMA-issue warp, 1 weight-producer warp.  Neighbour features are gathered with coalesced cp.async into per-warp staging rows; the final
+// THREE tiles in flight (this file) instead of two (mp_tc.cu): the tile chain (set-up, 4 x [GEMM, epilogue]) is
+// latency-bound, so throughput scales with the number of resident chains until the tensor / MUFU pipes fill.
+// TMEM holds 4 blocks of 128 columns: three tile "homes" and one floating block.  A tile's activations are written
+// IN PLACE over its accumulator (16 fp32 columns -> 8 columns of bf16 hi pairs + 8 of lo pairs), its next GEMM reads
+// them from the home and writes the floating block, which becomes the new home (the MMA warp publishes it in shared
+// memory before the commit); the old home is the next floating block.
+// CTA = 26 warps (72 registers): 24 epilogue warps (thread = edge row; 8 warps per tile = 4 TMEM lane quadrants x 2
+// column halves; the tiles share every weight load), 1 MMA-issue warp, 1 weight-producer warp.  Neighbour features
+// are gathered with coalesced cp.async into per-warp XOR-swizzled staging rows (no padding: 96 KB); the final
 // segmented sum walks the receiver-sorted rows in order (messages transposed through the staging tile, lane =
 // feature column) - no atomics, deterministic; rows that straddle a 32-edge block go to the `part` side buffer
 // and are summed (in order) by the node kernel.
@@ -27,18 +33,22 @@ using namespace tc;
 constexpr int TILE = 128;
 constexpr int WCHUNK = 32768;        // one weight part image (128 x 128 bf16)
 constexpr int RING = 4;
-constexpr int GROW = 80;             // staging row stride in bytes (64 data + 16 pad: conflict-free LDS.128)
-constexpr int EPI_WARPS = 16;        // 2 tiles in flight x 4 lane quadrants x 2 column halves
+constexpr int NSLOT = 3;             // tiles in flight
+constexpr int GROW = 64;             // staging row stride in bytes (un-padded; 16-byte chunks XOR-swizzled)
+constexpr int GBUF = 32 * GROW;      // one staging buffer: 32 rows x 64 B
+constexpr int EPI_WARPS = 8 * NSLOT; // tiles in flight x 4 lane quadrants x 2 column halves
 constexpr int MMA_WARP = EPI_WARPS;   // warp EPI_WARPS + 1 is the weight producer
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 
 struct __align__(1024) SmemTC {
   uint8_t w[RING][WCHUNK];
-  uint8_t gather[EPI_WARPS][2][32 * GROW];
+  uint8_t gather[EPI_WARPS][2][GBUF];
   float bias[4][128];
-  uint64_t full[RING], empty[RING], a_ready[2], d_ready[2];
+  uint64_t full[2], empty[2], a_ready[NSLOT], d_ready[NSLOT];
+  volatile uint32_t home[NSLOT];     // TMEM column block (0..3) holding the accumulator of the slot's GEMM in flight
   uint32_t tmem_base;
 };
+static_assert(sizeof(SmemTC) <= 232448, "shared memory budget (227 KB per CTA)");
 
 struct MpTcArgs {
   const uint8_t* w_img;   // [4 stages][2 parts][WCHUNK]
@@ -84,10 +94,12 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem
 
 // per-thread state of an epilogue thread for the tile it is working on
 struct EpiCtx {
-  uint32_t Dc, AH, AL;          // TMEM addresses (my lane quadrant, my 64-column half of my tile slot)
+  uint32_t Dc;                  // TMEM address: my lane quadrant, my 64-column half of my tile's current home block
   uint32_t gbuf[2];             // shared addresses of my warp's two gather staging buffers
   uint32_t grow_off;            // my row inside a staging buffer (lane * GROW)
-  uint32_t gl_dst;              // cp.async destination offset of this lane: (lane>>2)*GROW + (lane&3)*16
+  uint32_t gswz;                // XOR swizzle of my row's 16-byte chunks: (lane >> 1) & 3
+  uint32_t lane;
+  uint32_t gl_dst[4];           // cp.async destination offsets of this lane for rows (lane>>2) + 8*it (swizzled)
   int gl_row, gl_col;           // cp.async source row (lane>>2) and float offset ((lane&3)*4)
   uint32_t bias_addr;           // shared address of bias[0][col0]
   int col0, src;
@@ -102,12 +114,12 @@ struct EpiCtx {
 // 64 B of each of my warp's 32 neighbour rows, coalesced: 4 lanes per row, 8 rows per instruction
 __device__ __forceinline__ void issue_gather(const EpiCtx& c, int gi) {
   const float* base = (gi < 4 ? c.srcA : c.hn) + c.col0 + (gi & 3) * 16 + c.gl_col;
-  const uint32_t dst = c.gbuf[gi & 1] + c.gl_dst;
+  const uint32_t dst = c.gbuf[gi & 1];
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; it++) {
     const int sj = __shfl_sync(0xffffffffu, c.src, it * 8 + c.gl_row);
-    cp_async16s(dst + it * 8 * GROW, base + (size_t)sj * 128);
+    cp_async16s(dst + c.gl_dst[it], base + (size_t)sj * 128);
   }
   cp_async_commit();
 }
@@ -192,15 +204,15 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
         f32x2 X0 = add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y));
         f32x2 X1 = add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w));
         if (S == 1) {
-          const float4 sv = lds128(grow + j4 * 16);
+          const float4 sv = lds128(grow + ((j4 ^ c.gswz) << 4));
           X0 = add2(X0, add2(pk2(sv.x, sv.y), pk2(dc[j4].x, dc[j4].y)));
           X1 = add2(X1, add2(pk2(sv.z, sv.w), pk2(dc[j4].z, dc[j4].w)));
         }
         silu_split_pair(X0, h[2 * j4], l[2 * j4]);
         silu_split_pair(X1, h[2 * j4 + 1], l[2 * j4 + 1]);
       }
-      tmem_st8(c.AH + cc * 8, h);
-      tmem_st8(c.AL + cc * 8, l);
+      tmem_st8(c.Dc + cc * 16, h);        // in place over the accumulator chunk just read: [hi pairs | lo pairs]
+      tmem_st8(c.Dc + cc * 16 + 8, l);
       continue;
     }
     float x[16];
@@ -215,7 +227,7 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
     if (S == 1) {
 #pragma unroll
       for (int j4 = 0; j4 < 4; j4++) {
-        const float4 sv = lds128(grow + j4 * 16);
+        const float4 sv = lds128(grow + ((j4 ^ c.gswz) << 4));
         x[4 * j4] += sv.x + dc[j4].x;
         x[4 * j4 + 1] += sv.y + dc[j4].y;
         x[4 * j4 + 2] += sv.z + dc[j4].z;
@@ -227,19 +239,19 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
       if (EXACT) {
 #pragma unroll
         for (int j = 0; j < 8; j++) split_bf16(silu_fast(x[2 * j]), silu_fast(x[2 * j + 1]), h[j], l[j]);
-        tmem_st8(c.AH + cc * 8, h);
-        tmem_st8(c.AL + cc * 8, l);
+        tmem_st8(c.Dc + cc * 16, h);
+        tmem_st8(c.Dc + cc * 16 + 8, l);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; j++) h[j] = pack_bf16(silu_tanh(x[2 * j]), silu_tanh(x[2 * j + 1]));
-        tmem_st8(c.AH + cc * 8, h);
+        tmem_st8(c.Dc + cc * 16, h);
       }
     } else {
       // message = hn[src] * e_emb; parked (fp32) in my own accumulator columns until all four chunks are done
       uint32_t pr[16];
 #pragma unroll
       for (int j4 = 0; j4 < 4; j4++) {
-        const float4 hv = lds128(grow + j4 * 16);
+        const float4 hv = lds128(grow + ((j4 ^ c.gswz) << 4));
         pr[4 * j4] = __float_as_uint(c.valid ? x[4 * j4] * hv.x : 0.f);
         pr[4 * j4 + 1] = __float_as_uint(c.valid ? x[4 * j4 + 1] * hv.y : 0.f);
         pr[4 * j4 + 2] = __float_as_uint(c.valid ? x[4 * j4 + 2] * hv.z : 0.f);
@@ -253,8 +265,8 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
     // messages is transposed through my warp's (now idle) staging buffers, lane = feature column walks down the
     // rows in order and stores a finished receiver's 32 sums as one coalesced 128-byte row segment
     tmem_wait_st();
-    const uint32_t T = c.gbuf[0];              // 32 rows x 36 words (both staging buffers, 4608 B)
-    const uint32_t lane = c.grow_off / GROW;
+    const uint32_t T = c.gbuf[0];              // 32 rows x 128 B (both staging buffers, 4096 B), chunks XOR-swizzled
+    const uint32_t lane = c.lane;
 #pragma unroll 1
     for (int p = 0; p < 2; p++) {
       uint32_t v0[16], v1[16];
@@ -264,8 +276,8 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
       __syncwarp();
 #pragma unroll
       for (int j4 = 0; j4 < 4; j4++) {
-        sts128(T + lane * 144 + j4 * 16, v0[4 * j4], v0[4 * j4 + 1], v0[4 * j4 + 2], v0[4 * j4 + 3]);
-        sts128(T + lane * 144 + 64 + j4 * 16, v1[4 * j4], v1[4 * j4 + 1], v1[4 * j4 + 2], v1[4 * j4 + 3]);
+        sts128(T + lane * 128 + ((j4 ^ (lane & 7)) << 4), v0[4 * j4], v0[4 * j4 + 1], v0[4 * j4 + 2], v0[4 * j4 + 3]);
+        sts128(T + lane * 128 + (((4 + j4) ^ (lane & 7)) << 4), v1[4 * j4], v1[4 * j4 + 1], v1[4 * j4 + 2], v1[4 * j4 + 3]);
       }
       __syncwarp();
       float acc = 0.f;
@@ -273,7 +285,8 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
       for (int jb = 0; jb < 32; jb += 16) {
         float t[16];   // loads batched ahead of the (serial) add chain
 #pragma unroll
-        for (int j = 0; j < 16; j++) t[j] = lds32(T + (jb + j) * 144 + lane * 4);
+        for (int j = 0; j < 16; j++)
+          t[j] = lds32(T + (jb + j) * 128 + (((lane >> 2) ^ ((jb + j) & 7)) << 4) + (lane & 3) * 4);
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           acc += t[j];
@@ -289,24 +302,27 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
+template <bool SAFE_WAR>
+__global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc3(MpTcArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
-  SmemTC& sm = *reinterpret_cast<SmemTC*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  SmemTC& sm = *reinterpret_cast<SmemTC*>(raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0 && (smem_u32(raw) & 1023u)) __trap();   // SWIZZLE_128B weight images need 1024-byte alignment
   const int E = *a.n_edges;
   // tiles are addressed by SLOT: slot -> tile is the identity, or a look-up in the caller's tile list
   const int ntiles = a.tile_list ? *a.n_list : (E + TILE - 1) / TILE;
-  const int npairs = (ntiles + 1) / 2;
+  const int ngroups = (ntiles + NSLOT - 1) / NSLOT;      // a CTA works on NSLOT consecutive slots at a time
 
   if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base, 512);
   if (tid == 0) {
-    for (int i = 0; i < RING; i++) {
+    for (int i = 0; i < 2; i++) {
       mbar_init(&sm.full[i], 1);
-      mbar_init(&sm.empty[i], 2);   // both tile slots must have consumed a weight stage before it is replaced
+      mbar_init(&sm.empty[i], NSLOT);   // every tile slot must have consumed a weight stage before it is replaced
     }
-    for (int g = 0; g < 2; g++) {
+    for (int g = 0; g < NSLOT; g++) {
       mbar_init(&sm.a_ready[g], 256);
       mbar_init(&sm.d_ready[g], 1);
+      sm.home[g] = g;
     }
     fence_barrier_init();
   }
@@ -323,16 +339,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
     const bool exact = a.exact != 0;
     EpiCtx c;
     c.col0 = ch * 64;
-    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    c.Dc = tb + lane_base + g * 256 + c.col0;
-    c.AH = tb + lane_base + g * 256 + 128 + c.col0 / 2;
-    c.AL = c.AH + 64;
+    const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + c.col0;
+    c.Dc = tb + lane_base + g * 128;          // the slot's first home block is block g
     c.gbuf[0] = smem_u32(sm.gather[warp][0]);
     c.gbuf[1] = smem_u32(sm.gather[warp][1]);
+    c.lane = lane;
     c.grow_off = lane * GROW;
+    c.gswz = (lane >> 1) & 3;
     c.gl_row = lane >> 2;
     c.gl_col = (lane & 3) * 4;
-    c.gl_dst = (lane >> 2) * GROW + (lane & 3) * 16;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int row = it * 8 + (lane >> 2);
+      c.gl_dst[it] = row * GROW + ((((uint32_t)lane & 3u) ^ (((uint32_t)row >> 1) & 3u)) << 4);
+    }
     c.bias_addr = smem_u32(&sm.bias[0][c.col0]);
     c.srcA = a.srcA;
     c.hn = a.hn;
@@ -345,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
     int nsrc = 0, ndst = -1;
     int next_tile = -1;
     {
-      const int s0 = blockIdx.x * 2 + g;
+      const int s0 = blockIdx.x * NSLOT + g;
       if (s0 < ntiles) next_tile = a.tile_list ? __ldg(a.tile_list + s0) : s0;
       const int e_first = next_tile * TILE + r;
       if (next_tile >= 0 && e_first < E) {
@@ -353,8 +373,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
         ndst = a.edst[e_first];
       }
     }
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int slot = pair * 2 + g;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+      const int slot = grp * NSLOT + g;
       if (slot >= ntiles) continue;
       const int tile = next_tile;
       const bool dbg_on = dbg_rec && blockIdx.x == 0 && lane == 0 && dbg_n + 14 <= 256;
@@ -370,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
 #pragma unroll
       for (int i = 0; i < 8; i++) q[i] = __ldg(bh + i * 128);
       {  // the next tile of this slot and the endpoints of my edge in it
-        const int nslot = slot + 2 * (int)gridDim.x;
+        const int nslot = slot + NSLOT * (int)gridDim.x;
         next_tile = -1;
         if (nslot < ntiles) next_tile = a.tile_list ? __ldg(a.tile_list + nslot) : nslot;
         const int en = next_tile * TILE + r;
@@ -395,7 +415,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
         }
       }
 
-      // ---- stage 0 operand: my half of the e tile (bf16 hi / lo) -> TMEM A ------------------
+      // ---- stage 0 operand: my half of the e tile -> my 64 columns of the home block, K step j at columns 16 j:
+      //      [8 columns of bf16 hi pairs | 8 columns of lo pairs] (the layout every epilogue writes in place) ----
       {
 #pragma unroll
         for (int part = 0; part < 2; part++) {
@@ -405,14 +426,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
             for (int i = 0; i < 8; i++) q[i] = __ldg(bh + 32768 / 16 + i * 128);
           }
 #pragma unroll
-          for (int c2 = 0; c2 < 2; c2++) {
-            uint32_t h[16];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              h[4 * i] = q[c2 * 4 + i].x; h[4 * i + 1] = q[c2 * 4 + i].y;
-              h[4 * i + 2] = q[c2 * 4 + i].z; h[4 * i + 3] = q[c2 * 4 + i].w;
-            }
-            tmem_st16((part ? c.AL : c.AH) + c2 * 16, h);
+          for (int j = 0; j < 4; j++) {
+            const uint32_t h[8] = {q[2 * j].x, q[2 * j].y, q[2 * j].z, q[2 * j].w,
+                                   q[2 * j + 1].x, q[2 * j + 1].y, q[2 * j + 1].z, q[2 * j + 1].w};
+            tmem_st8(c.Dc + j * 16 + part * 8, h);
           }
         }
         tmem_wait_st();
@@ -436,11 +453,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
         c.out_row += c.col0;
       }
 
+      // the GEMM of a stage writes the floating block; the MMA warp publishes which one before it commits
 #define GAMD_STAGE(S)                              \
   if (dbg_on) dbg_rec[dbg_n++] = clock64();        \
   mbar_wait(d_bar, d_par);                         \
   d_par ^= 1;                                      \
   tc_fence_after();                                \
+  c.Dc = tb + lane_base + sm.home[g] * 128u;       \
   if (dbg_on) dbg_rec[dbg_n++] = clock64();        \
   if (exact) stage_epilogue<S, true>(c);           \
   else stage_epilogue<S, false>(c);                \
@@ -457,35 +476,63 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
 #undef GAMD_STAGE
     }
   } else if (warp == MMA_WARP) {
-    // ===================== MMA issue (one thread): an event loop over the two tiles in flight =====================
-    // (A single thread issues a tcgen05.mma only every ~120 cycles - tc_ubench.cu - so a 24-MMA stage costs ~2.9k
-    // cycles of issue.  Variants with one issuer per tile slot, two issuers per stage, or K steps issued as the
-    // previous epilogue publishes 16-column chunks were all measured SLOWER: they let the two tiles fall into
-    // lockstep on the MUFU pipe; two issuers per accumulator also lose run-to-run determinism.)
-    // Each tile slot walks its own sequence of (pair, stage) steps Q = 4 * pair_iteration + stage and is served as
-    // soon as its A operand is in TMEM and the weights of that stage are in shared memory, independently of the
-    // other slot.  bf16x3: weights live in two slot pairs (hi, lo) indexed by Q & 1; a pair is reloaded with stage
-    // Q + 2 once BOTH tiles have consumed stage Q (wempty counts 2), so the slots may drift apart by one stage.
+    // ===================== MMA issue: an event loop over the tiles in flight =====================
+    // Each tile slot walks its own sequence of (group, stage) steps Q = 4 * group_iteration + stage and is served as
+    // soon as its A operand is in TMEM and the weights of that stage are in shared memory, independently of the other
+    // slots (round-robin from the slot after the one served last).  bf16x3: weights live in two slot pairs (hi, lo)
+    // indexed by Q & 1; a pair is reloaded with stage Q + 2 once ALL tiles have consumed stage Q (empty counts NSLOT),
+    // so the slots may drift apart by one stage.  A GEMM reads its A operand from the slot's home block and writes the
+    // floating block; afterwards the roles swap.  The next GEMM therefore overwrites the block the previous one reads:
+    // SAFE_WAR waits for the previous commit first (tcgen05.mma of one thread execute in issue order, so this is
+    // belt and braces; the variant without the wait is kept for measurement).
     // The whole warp runs the loop on warp-uniform values; only the MMAs, commits and arrives are predicated on one
     // elected lane (see tc_common.cuh: issuing from inside `if (lane == 0)` halves the MMA issue rate).
     {
       const uint32_t leader = elect_leader();
       const uint32_t idesc = umma_idesc_bf16(128, 128);
-      const int n_my_pairs = blockIdx.x < npairs ? (npairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-      const int totalQ = 4 * n_my_pairs;
-      int Qg[2] = {0, 0};
-      uint32_t a_par[2] = {0, 0};
-      bool w_res = false;   // bf16 mode: all four hi images resident after the first load
-      uint32_t spins = 0;
-      while (Qg[0] < totalQ || Qg[1] < totalQ) {
-        bool progressed = false;
+      const int n_my_groups = blockIdx.x < ngroups ? (ngroups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+      const int totalQ = 4 * n_my_groups;
+      // per-slot state lives in registers: every loop over the slots is fully unrolled with static indices
+      int Qg[NSLOT];
+      uint32_t a_par[NSLOT], home[NSLOT];
 #pragma unroll
-        for (int g = 0; g < 2; g++) {
+      for (int g = 0; g < NSLOT; g++) {
+        Qg[g] = 0;
+        a_par[g] = 0;
+        home[g] = g;
+      }
+      uint32_t floating = NSLOT;
+      uint32_t last_bar = 0, last_par = 0;   // d_ready barrier / parity of the GEMM issued last (guards the block it read)
+      int first = 0;                         // round-robin start
+      bool w_res = false;                    // bf16 mode: all four hi images resident after the first load
+      uint32_t spins = 0;
+      uint32_t c_par_bits = 0;               // bit g: parity of slot g's next commit on d_ready
+      for (;;) {
+        bool done = true;
+#pragma unroll
+        for (int g = 0; g < NSLOT; g++) done = done && Qg[g] >= totalQ;
+        if (done) break;
+        bool progressed = false;
+        // the floating block is the A operand of the GEMM issued last: it may be overwritten once that GEMM completed
+        bool war_ok = true;
+        if (SAFE_WAR && last_bar) {
+          uint32_t ok;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}"
+              : "=r"(ok)
+              : "r"(last_bar), "r"(last_par)
+              : "memory");
+          war_ok = __all_sync(0xffffffffu, ok != 0);
+        }
+        int pick = -1, best = NSLOT;
+#pragma unroll
+        for (int g = 0; g < NSLOT; g++) {
           const int Q = Qg[g];
           if (Q >= totalQ) continue;
-          const int s = Q & 3;
-          const int pair = blockIdx.x + (Q >> 2) * gridDim.x;
-          const bool tile_valid = pair * 2 + g < ntiles;
+          const int grp = blockIdx.x + (Q >> 2) * gridDim.x;
+          const bool tile_valid = grp * NSLOT + g < ntiles;
           const int sp = Q & 1;
           if (a.exact) {
             if (!__all_sync(0xffffffffu, mbar_test_wait(&sm.full[sp], (Q >> 1) & 1))) continue;
@@ -493,26 +540,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
             if (!__all_sync(0xffffffffu, mbar_test_wait(&sm.full[0], 0))) continue;
             w_res = true;
           }
-          if (!tile_valid) {          // absent second tile of the tail pair: release the weights on its behalf
+          if (!tile_valid) {          // absent tile of the tail group: release the weights on its behalf
             if (a.exact && leader) mbar_arrive(&sm.empty[sp]);
             Qg[g]++;
             progressed = true;
             continue;
           }
+          if (!war_ok) continue;
           if (!__all_sync(0xffffffffu, mbar_test_wait(&sm.a_ready[g], a_par[g]))) continue;
+          int pr = g - first;
+          if (pr < 0) pr += NSLOT;
+          if (pr < best) {
+            best = pr;
+            pick = g;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < NSLOT; g++) {
+          if (g != pick) continue;
+          const int Q = Qg[g];
+          const int s = Q & 3, sp = Q & 1;
           a_par[g] ^= 1;
           tc_fence_after();
           const uint32_t bhi = smem_u32(a.exact ? sm.w[2 * sp] : sm.w[s]);
           const uint32_t blo = smem_u32(sm.w[2 * sp + 1]);
-          const uint32_t d = tb + g * 256, ah = d + 128, al = d + 192;
+          const uint32_t d = tb + floating * 128u, ab = tb + home[g] * 128u;
+          if (leader) sm.home[g] = floating;       // read by the slot's epilogue threads after the commit arrives
+          __threadfence_block();
           const int passes = a.exact ? 3 : 1;
           uint32_t accum = 0;
           for (int p = 0; p < passes; p++) {
             const uint32_t bb = (p == 2) ? blo : bhi;
-            const uint32_t aa = (p == 1) ? al : ah;
+            const uint32_t aa = ab + ((p == 1) ? 8u : 0u);
 #pragma unroll
             for (int ks = 0; ks < 8; ks++) {
-              umma_ts_elect(d, aa + ks * 8, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum,
+              umma_ts_elect(d, aa + ks * 16, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum,
                             leader);
               accum = 1;
             }
@@ -522,6 +584,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
             if (a.exact) umma_commit(&sm.empty[sp]);
           }
           __syncwarp();
+          last_bar = smem_u32(&sm.d_ready[g]);
+          last_par = (c_par_bits >> g) & 1u;
+          c_par_bits ^= 1u << g;
+          const uint32_t old_home = home[g];
+          home[g] = floating;
+          floating = old_home;
+          first = g + 1 == NSLOT ? 0 : g + 1;
           Qg[g]++;
           progressed = true;
         }
@@ -533,9 +602,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
   } else {
     // ===================== weight producer (one thread) =====================
     if (lane == 0) {
-      const int n_my_pairs = blockIdx.x < npairs ? (npairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+      const int n_my_groups = blockIdx.x < ngroups ? (ngroups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       if (!a.exact) {
-        if (n_my_pairs) {
+        if (n_my_groups) {
           mbar_arrive_expect_tx(&sm.full[0], 4 * WCHUNK);
           for (int s = 0; s < 4; s++)
 #pragma unroll
@@ -543,7 +612,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
               bulk_g2s(sm.w[s] + i * 8192, a.w_img + (size_t)s * 2 * WCHUNK + i * 8192, 8192, &sm.full[0]);
         }
       } else {
-        const int totalQ = 4 * n_my_pairs;
+        const int totalQ = 4 * n_my_groups;
         for (int Q = 0; Q < totalQ; Q++) {
           const int sp = Q & 1, n = Q >> 1;
           if (n >= 1) mbar_wait(&sm.empty[sp], (n - 1) & 1);
@@ -563,15 +632,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
 
 }  // namespace
 
-int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which) {
-  // GAMD_MP_VARIANT (read at gamd_create): 3 = three tiles in flight (mp_tc3.cu), 4 = the same without the commit wait
-  if (ctx->mp_variant == 3 || ctx->mp_variant == 4) return mp_edge_tc3_launch(ctx, layer, st, which, ctx->mp_variant == 3);
-  // 5 = CTA pairs (cta_group::2) with resident weights, three tiles in flight (mp_tc2cta.cu); 6 = without the commit wait
-  if (ctx->mp_variant == 5 || ctx->mp_variant == 6) return mp_edge_tc2_launch(ctx, layer, st, which, ctx->mp_variant == 5);
-  const size_t smem = sizeof(SmemTC) + 1024;
-  if (!(ctx->attr_mask & GAMD_ATTR_MP_TC)) {
-    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->attr_mask |= GAMD_ATTR_MP_TC;
+// three tiles in flight per SM (see the header of this file); safe_war: wait for the previous GEMM's commit before
+// a GEMM overwrites the TMEM block that one read as its A operand
+int mp_edge_tc3_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war) {
+  const size_t smem = sizeof(SmemTC);
+  if (!(ctx->attr_mask & GAMD_ATTR_MP_TC3)) {
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->attr_mask |= GAMD_ATTR_MP_TC3;
   }
   MpTcArgs a;
   a.w_img = ctx->d_wimg + (size_t)layer * 8 * WCHUNK;
@@ -593,7 +661,8 @@ int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which) {
   // interior launch of a tile-split layer: optionally leave a few SMs to the halo exchange running beside it
   const int reserve = ctx->dd_reserve_sms;
   const int grid = which == 0 && reserve > 0 && reserve < ctx->sm_count ? ctx->sm_count - reserve : ctx->sm_count;
-  k_mp_edge_tc<<<grid, THREADS, smem, st>>>(a);
+  if (safe_war) k_mp_edge_tc3<true><<<grid, THREADS, smem, st>>>(a);
+  else k_mp_edge_tc3<false><<<grid, THREADS, smem, st>>>(a);
   GAMD_LAUNCH_CHECK();
   return 0;
 }

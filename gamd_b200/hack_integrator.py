@@ -9,13 +9,17 @@ fp64 state through the C ABI (``gamd_vv_first_half`` / ``gamd_vv_second_half``);
 driver scripts touch (code/LJ/test_script/test_nosehoover.py:41-57, 100-118).
 
 Units are OpenMM's: nm, ps, Da, K, kJ/mol; quantities are plain floats (objects with ``value_in_unit_system``
-are unwrapped when simtk/openmm is importable).  Constraints (SETTLE) are not built - SURVEY.md 8f rank 2.
+are unwrapped when simtk/openmm is importable).  ``System(..., rigid_water=True)`` holds [O,H,H] triplets rigid
+with the analytic SETTLE kernels (``gamd_settle_positions`` / ``gamd_settle_velocities``), the stand-in for OpenMM's
+ConstrainPositions / ConstrainVelocities on ``WaterBox(constrained=True)`` systems.
 
   HackNoseHooverIntegrator      :182-330   propagateNHC; v+=0.5*dt*force_last/m; x+=dt*v
   HackHalfNoseHooverIntegrator  :334-493   v+=0.5*dt*gnn_force/m; propagateNHC; bath energies
   HackLangevinIntegrator        :90-169    B, A/2, O, A/2
   HackHalfVelocityIntegrator    :171-178   v+=(dt/2)*gnn_force/m
   HackAndersenVVIntegrator      :17-86     per-particle Andersen collisions + VV with test1/test2 forces
+  water-only (code/water/hack_integrator.py): HackIntegratorNHC :18-177, HackDummyIntegrator :180-188,
+  HackDummyIntegratorNHC :193-347
 """
 import numpy as np
 import torch
@@ -45,8 +49,11 @@ def _val(q):
 class System:
     """masses in Da; the only OpenMM ``System`` facts the hook needs."""
 
-    def __init__(self, masses, n_constraints=0, has_cm_motion_remover=False):
+    def __init__(self, masses, n_constraints=0, has_cm_motion_remover=False, rigid_water=False):
         self.masses = np.asarray(masses, dtype=np.float64)
+        self.rigid_water = bool(rigid_water)
+        if self.rigid_water and n_constraints == 0:
+            n_constraints = len(self.masses)          # three distance constraints per [O,H,H] molecule
         self.n_constraints = n_constraints
         self.has_cm_motion_remover = has_cm_motion_remover
 
@@ -91,6 +98,24 @@ class Context:
         self.gen = torch.Generator(device=self.dev)
         self.gen.manual_seed(0)
         self.lib = neighbor_context(self.dev.index or 0)
+        # constrained=True water (code/water/test_script/test_nosehoover.py:33-37): [O,H,H] triplets held rigid by SETTLE
+        self.rigid_water = bool(getattr(system, "rigid_water", False))
+        self.x_ref = torch.zeros_like(self.x) if self.rigid_water else None
+
+    # ---- the two kick programs every Hack* class is built from ----
+    def first_half_kick_drift(self, force, dt):
+        """v += 0.5 dt f/m; x += dt v; x1 = x; constrain positions; v += (x - x1)/dt  (hack_integrator.py:273-277)."""
+        if self.rigid_water:
+            self.x_ref.copy_(self.x)
+        self.lib.vv_first_half(self.x, self.v, force, self.mass, dt)
+        if self.rigid_water:
+            self.lib.settle_positions(self.x_ref, self.x, self.mass, v=self.v, dt_corr=dt)
+
+    def second_half_kick(self, force, dt):
+        """v += 0.5 dt f/m; constrain velocities  (hack_integrator.py:421-422, :175-178)."""
+        self.lib.vv_second_half(self.v, force, self.mass, dt)
+        if self.rigid_water:
+            self.lib.settle_velocities(self.x, self.v, self.mass)
 
     def setPositions(self, pos_nm):
         self.x.copy_(torch.as_tensor(np.asarray(pos_nm, dtype=np.float64)))
@@ -166,7 +191,13 @@ class _HackIntegrator:
 
 
 class _NHCMixin:
+    """Nose-Hoover chain of one integrator object: a device-resident ``gamd_nhc_state`` (xi, vxi, G, Q, scale, KE2,
+    bath energies) propagated by one CUDA thread from a device-side kinetic-energy reduction
+    (``gamd_nhc_propagate`` = propagateNHC, hack_integrator.py:289-316) - no host synchronisation per half step.
+    ``getGlobalVariableByName`` reads the state back on demand; ``copy_state_from_integrator`` is a device-to-device
+    copy of the chain variables (hack_integrator.py:322-330, :440-452)."""
     YSWeights = YS_WEIGHTS
+    _CHAIN_GLOBALS = ("xi", "vxi", "G", "Q")
 
     def _init_nhc(self, system, collision_frequency, chain_length, num_mts, num_yoshidasuzuki):
         self.n_c, self.n_ys = num_mts, num_yoshidasuzuki
@@ -174,116 +205,167 @@ class _NHCMixin:
             raise Exception("Invalid Yoshida-Suzuki value. Allowed values are: %s" % ",".join(map(str, YS_WEIGHTS)))
         if chain_length < 0:
             raise Exception("Nose-Hoover chain length must be at least 0")
+        if chain_length > _capi.NHC_MAX:
+            raise Exception("Nose-Hoover chain length above %d is not built" % _capi.NHC_MAX)
         self.weights = YS_WEIGHTS[self.n_ys]
         self.M = chain_length
-        frequency = _val(collision_frequency)
-        q = self.kT / frequency ** 2
-        ndf = system.ndf() if system is not None else None
-        g = self._globals
-        g.update(ndf=ndf, bathKE=0.0, bathPE=0.0, KE2=0.0, Q=q, scale=1.0)
-        for i in range(self.M):
-            g[f"xi{i}"] = 0.0
-            g[f"vxi{i}"] = 0.0
-            g[f"G{i}"] = -frequency ** 2
-            # Q1..Q{M-1} = Q always (the reference sets them inside the step program, hack_integrator.py:283-287);
-            # Q0 = ndf * Q is fixed in propagateNHC when the system (ndf) is only known at bind time
-            g[f"Q{i}"] = q if i else (ndf * q if ndf is not None else 0.0)
+        self._frequency = _val(collision_frequency)
+        self._ndf = system.ndf() if system is not None else None
+        self._globals.update(ndf=self._ndf, Q=self.kT / self._frequency ** 2)
+        self._state = None            # device buffer, created at bind time (needs the context's library handle)
+        self._pending = {}            # globals set before bind
 
-    def propagateNHC(self):
-        """hack_integrator.py:289-316 / :454-481: chain scalars on the host, one KE reduction and one
-        velocity scaling on the device."""
-        M, g, ctx = self.M, self._globals, self.context
-        if not M:
-            return
-        if g["ndf"] is None:
-            g["ndf"] = 3 * ctx.system.getNumParticles()
-            g["Q0"] = g["ndf"] * g["Q"]
-        ke2 = float((ctx.mass[:, None] * ctx.v * ctx.v).sum().item())
-        g["KE2"] = ke2
-        kT, ndf, dt = self.kT, g["ndf"], self.dt
-        xi = [g[f"xi{i}"] for i in range(M)]
-        vxi = [g[f"vxi{i}"] for i in range(M)]
-        G = [g[f"G{i}"] for i in range(M)]
-        Q = [g[f"Q{i}"] for i in range(M)]
-        scale = 1.0
-        G[0] = (ke2 - ndf * kT) / Q[0]
-        for _ in range(self.n_c):
-            for w in self.weights:
-                wdt = w * dt / self.n_c
-                vxi[M - 1] += 0.25 * wdt * G[M - 1]
-                for j in range(M - 2, -1, -1):
-                    aa = np.exp(-0.125 * wdt * vxi[j + 1])
-                    vxi[j] = aa * (aa * vxi[j] + 0.25 * wdt * G[j])
-                aa = np.exp(-0.5 * wdt * vxi[0])
-                scale *= aa
-                for j in range(M):
-                    xi[j] += 0.5 * wdt * vxi[j]
-                G[0] = (scale * scale * ke2 - ndf * kT) / Q[0]
-                for j in range(M - 1):
-                    aa = np.exp(-0.125 * wdt * vxi[j + 1])
-                    vxi[j] = aa * (aa * vxi[j] + 0.25 * wdt * G[j])
-                    G[j + 1] = (Q[j] * vxi[j] * vxi[j] - kT) / Q[j + 1]
-                vxi[M - 1] += 0.25 * wdt * G[M - 1]
-        for i in range(M):
-            g[f"xi{i}"], g[f"vxi{i}"], g[f"G{i}"] = xi[i], vxi[i], G[i]
-        g["scale"] = scale
-        ctx.v.mul_(scale)
+    def bind(self, context):
+        super().bind(context)
+        if self._ndf is None:         # "system was not passed": ndf = number of DOFs (hack_integrator.py:225-231)
+            self._ndf = 3 * context.system.getNumParticles()
+            self._globals["ndf"] = self._ndf
+        self._state = context.lib.nhc_new_state(self.M, self.n_c, self.n_ys, self.kT, self._frequency, self._ndf)
+        for k, v in self._pending.items():
+            self.setGlobalVariableByName(k, v)
+        self._pending = {}
+
+    def _host_state(self):
+        return self.context.lib.nhc_get_state(self._state)
+
+    def getGlobalVariableByName(self, name):
+        for base in self._CHAIN_GLOBALS:
+            if name.startswith(base) and name[len(base):].isdigit() and self._state is not None:
+                return float(getattr(self._host_state(), base)[int(name[len(base):])])
+        if name in ("bathKE", "bathPE", "scale") and self._state is not None:
+            return float(getattr(self._host_state(), name))
+        if name == "KE2" and self._state is not None:
+            return float(self._host_state().ke2_in)
+        return self._globals[name]
+
+    def setGlobalVariableByName(self, name, value):
+        for base in self._CHAIN_GLOBALS + ("bathKE", "bathPE"):
+            idx = name[len(base):]
+            if name.startswith(base) and (idx.isdigit() or (idx == "" and base.startswith("bath"))):
+                if self._state is None:
+                    self._pending[name] = float(value)
+                    return
+                h = self._host_state()
+                if idx:
+                    getattr(h, base)[int(idx)] = float(value)
+                else:
+                    setattr(h, base, float(value))
+                self.context.lib.nhc_set_state(h, self._state)
+                return
+        self._globals[name] = float(value)
+
+    def propagateNHC(self, bath=False):
+        """hack_integrator.py:289-316 / :454-481 on the device (KE2 reduction, chain, v *= scale)."""
+        if self.M:
+            c = self.context
+            c.lib.nhc_propagate(c.v, c.mass, self.dt, state=self._state, bath=bath)
 
     def copy_state_from_integrator(self, integrator):
-        names = ["bathKE", "bathPE"] if isinstance(self, HackHalfNoseHooverIntegrator) else []
-        for i in range(self.M):
-            names += [f"xi{i}", f"vxi{i}", f"G{i}", f"Q{i}"]
-        for nme in names:
-            self.setGlobalVariableByName(nme, integrator.getGlobalVariableByName(nme))
+        """chain variables xi, vxi, G, Q (and the bath energies for the second-half class) from the other
+        integrator: a device-to-device copy of the state record, no host round trip."""
+        if self._state is None or integrator._state is None:
+            raise RuntimeError("copy_state_from_integrator needs both integrators bound to a Simulation")
+        keep = self._host_state() if not isinstance(self, HackHalfNoseHooverIntegrator) else None
+        self._state.copy_(integrator._state)
+        if keep is not None:          # the first-half class does not copy bathKE / bathPE (hack_integrator.py:322-330)
+            h = self._host_state()
+            h.bathKE, h.bathPE = keep.bathKE, keep.bathPE
+            self.context.lib.nhc_set_state(h, self._state)
 
 
-class HackNoseHooverIntegrator(_HackIntegrator, _NHCMixin):
-    """first half: propagateNHC; v += 0.5*dt*force_last/m; x += dt*v (hack_integrator.py:267-277)."""
+class HackNoseHooverIntegrator(_NHCMixin, _HackIntegrator):
+    """first half: propagateNHC; v += 0.5*dt*force_last/m; x += dt*v; constrain positions; v += (x-x1)/dt
+    (hack_integrator.py:267-277)."""
     PER_DOF = ("force_last", "x1")
 
     def __init__(self, system=None, temperature=298.0, collision_frequency=50.0, timestep=0.001, chain_length=5,
                  num_mts=5, num_yoshidasuzuki=5):
-        super().__init__(temperature, timestep)
+        _HackIntegrator.__init__(self, temperature, timestep)
         self._init_nhc(system, collision_frequency, chain_length, num_mts, num_yoshidasuzuki)
 
     def _step(self):
         c = self.context
         self.propagateNHC()
-        c.lib.vv_first_half(c.x, c.v, self._perdof["force_last"], c.mass, self.dt)
+        c.first_half_kick_drift(self._perdof["force_last"], self.dt)
 
 
-class HackHalfNoseHooverIntegrator(_HackIntegrator, _NHCMixin):
-    """second half: v += 0.5*dt*gnn_force/m; propagateNHC; bath energies (hack_integrator.py:419-425)."""
+class HackHalfNoseHooverIntegrator(_NHCMixin, _HackIntegrator):
+    """second half: v += 0.5*dt*gnn_force/m; constrain velocities; propagateNHC; bath energies
+    (hack_integrator.py:419-425)."""
     PER_DOF = ("gnn_force", "x1")
 
     def __init__(self, system=None, temperature=298.0, collision_frequency=50.0, timestep=0.001, chain_length=5,
                  num_mts=5, num_yoshidasuzuki=5):
-        super().__init__(temperature, timestep)
+        _HackIntegrator.__init__(self, temperature, timestep)
         self._init_nhc(system, collision_frequency, chain_length, num_mts, num_yoshidasuzuki)
 
     def _step(self):
-        c, g = self.context, self._globals
-        c.lib.vv_second_half(c.v, self._perdof["gnn_force"], c.mass, self.dt)
+        c = self.context
+        c.second_half_kick(self._perdof["gnn_force"], self.dt)
+        self.propagateNHC(bath=True)
+
+
+class HackIntegratorNHC(_NHCMixin, _HackIntegrator):
+    """water-only class (code/water/hack_integrator.py:18-177): the whole thermostatted velocity-Verlet step with both
+    forces given: propagateNHC; v += 0.5 dt test1/m; x += dt v; constrain; v += 0.5 dt test2/m + (x-x1)/dt; constrain v;
+    propagateNHC; bath energies."""
+    PER_DOF = ("test1", "test2", "x1")
+
+    def __init__(self, system=None, temperature=298.0, collision_frequency=50.0, timestep=0.001, chain_length=5,
+                 num_mts=5, num_yoshidasuzuki=5):
+        _HackIntegrator.__init__(self, temperature, timestep)
+        self._init_nhc(system, collision_frequency, chain_length, num_mts, num_yoshidasuzuki)
+
+    def _step(self):
+        c = self.context
         self.propagateNHC()
-        g["bathKE"] = sum(0.5 * g[f"Q{i}"] * g[f"vxi{i}"] ** 2 for i in range(self.M))
-        if self.M:
-            g["bathPE"] = self.kT * (g["ndf"] * g["xi0"] + sum(g[f"xi{i}"] for i in range(1, self.M)))
+        c.first_half_kick_drift(self._perdof["test1"], self.dt)
+        c.second_half_kick(self._perdof["test2"], self.dt)
+        self.propagateNHC(bath=True)
+
+
+class HackDummyIntegrator(_HackIntegrator):
+    """water-only class (code/water/hack_integrator.py:180-188): zero time step, constraints only."""
+
+    def __init__(self):
+        super().__init__(0.0, 0.0)
+
+    def _step(self):
+        c = self.context
+        if c.rigid_water:
+            c.lib.settle_positions(c.x_ref, c.x, c.mass)
+            c.x_ref.copy_(c.x)
+            c.lib.settle_velocities(c.x, c.v, c.mass)
+
+
+class HackDummyIntegratorNHC(_NHCMixin, _HackIntegrator):
+    """water-only class (code/water/hack_integrator.py:193-347): the chain propagation alone (thermostat scale
+    without moving the atoms)."""
+
+    def __init__(self, system=None, temperature=298.0, collision_frequency=50.0, timestep=0.001, chain_length=5,
+                 num_mts=5, num_yoshidasuzuki=5):
+        _HackIntegrator.__init__(self, temperature, timestep)
+        self._init_nhc(system, collision_frequency, chain_length, num_mts, num_yoshidasuzuki)
+
+    def _step(self):
+        self.propagateNHC()
 
 
 class HackHalfVelocityIntegrator(_HackIntegrator):
-    """v += (dt/2)*gnn_force/m (hack_integrator.py:171-178)."""
+    """v += (dt/2)*gnn_force/m; constrain velocities (hack_integrator.py:171-178)."""
     PER_DOF = ("gnn_force",)
 
     def __init__(self, timestep):
         super().__init__(0.0, timestep)
 
     def _step(self):
-        c = self.context
-        c.lib.vv_second_half(c.v, self._perdof["gnn_force"], c.mass, self.dt)
+        self.context.second_half_kick(self._perdof["gnn_force"], self.dt)
 
 
 class HackLangevinIntegrator(_HackIntegrator):
-    """B, A/2, O, A/2 with the injected force (hack_integrator.py:141-165), no constraints."""
+    """B, A/2, O, A/2 with the injected force (hack_integrator.py:141-165).  One fused kernel without constraints
+    (``gamd_langevin_first_half``, Philox4x32-10 noise); with rigid water every sub-step is followed by its
+    constraint stage exactly as the per-DOF program lists them."""
     PER_DOF = ("force_last", "x1", "sigma")
 
     def __init__(self, temperature=298.0, collision_rate=1.0, timestep=0.001, constraint_tolerance=1e-8):
@@ -291,35 +373,46 @@ class HackLangevinIntegrator(_HackIntegrator):
         self._gamma = _val(collision_rate)
         self._globals["a"] = float(np.exp(-self._gamma * self.dt))
         self._globals["b"] = float(np.sqrt(1 - np.exp(-2 * self._gamma * self.dt)))
+        self.injected_gaussian = None        # tests: [N,3] standard normals instead of the Philox stream
 
     def _step(self):
         c, g = self.context, self._globals
-        sigma = torch.sqrt(self.kT / c.mass)[:, None]
-        c.v.add_(self._perdof["force_last"] / c.mass[:, None], alpha=self.dt / 2)
-        c.x.add_(c.v, alpha=self.dt / 2)
-        noise = torch.randn(c.x.shape, dtype=torch.float64, device=c.dev, generator=c.gen)
-        c.v.mul_(g["a"]).add_(sigma * noise, alpha=g["b"])
-        c.x.add_(c.v, alpha=self.dt / 2)
+        f = self._perdof["force_last"]
+        if not c.rigid_water:
+            c.lib.langevin_first_half(c.x, c.v, f, c.mass, self.dt, self.kT, self._gamma, gaussian=self.injected_gaussian)
+            return
+        h = self.dt / 2
+        noise = self.injected_gaussian
+        if noise is None:
+            noise = torch.randn(c.x.shape, dtype=torch.float64, device=c.dev, generator=c.gen)
+        c.lib.vv_second_half(c.v, f, c.mass, self.dt)                       # B: v += (dt/2) f/m
+        c.lib.settle_velocities(c.x, c.v, c.mass)
+        for stage in range(2):                                              # A, O, A
+            c.x_ref.copy_(c.x)
+            c.x.add_(c.v, alpha=h)
+            c.lib.settle_positions(c.x_ref, c.x, c.mass, v=c.v, dt_corr=h)
+            c.lib.settle_velocities(c.x, c.v, c.mass)
+            if stage == 0:
+                c.v.mul_(g["a"]).add_(torch.sqrt(self.kT / c.mass)[:, None] * noise, alpha=g["b"])
+                c.lib.settle_velocities(c.x, c.v, c.mass)
 
 
 class HackAndersenVVIntegrator(_HackIntegrator):
-    """per-particle Andersen collisions, then v+=0.5*dt*test1/m; x+=dt*v; v+=0.5*dt*test2/m
-    (hack_integrator.py:66-86)."""
+    """per-DOF Andersen collisions (``gamd_andersen_collide``), then v+=0.5*dt*test1/m; x+=dt*v; constrain;
+    v+=0.5*dt*test2/m+(x-x1)/dt; constrain v (hack_integrator.py:66-86)."""
     PER_DOF = ("test1", "test2", "x1", "sigma_v", "collision")
 
     def __init__(self, temperature=298.0, collision_rate=91.0, timestep=0.001):
         super().__init__(temperature, timestep)
         self._globals["p_collision"] = self.dt * _val(collision_rate)
+        self.injected_uniform = self.injected_gaussian = None
 
     def _step(self):
         c = self.context
-        sigma_v = torch.sqrt(self.kT / c.mass)[:, None]
-        u = torch.rand(c.x.shape, dtype=torch.float64, device=c.dev, generator=c.gen)
-        gauss = torch.randn(c.x.shape, dtype=torch.float64, device=c.dev, generator=c.gen)
-        coll = (self._globals["p_collision"] - u >= 0).to(torch.float64)      # step(p_collision - uniform)
-        c.v.copy_((1 - coll) * c.v + coll * sigma_v * gauss)
-        c.lib.vv_first_half(c.x, c.v, self._perdof["test1"], c.mass, self.dt)
-        c.lib.vv_second_half(c.v, self._perdof["test2"], c.mass, self.dt)
+        c.lib.andersen_collide(c.v, c.mass, self.kT, self._globals["p_collision"], uniform=self.injected_uniform,
+                               gaussian=self.injected_gaussian)
+        c.first_half_kick_drift(self._perdof["test1"], self.dt)
+        c.second_half_kick(self._perdof["test2"], self.dt)
 
 
 class CompoundIntegrator:

@@ -172,6 +172,67 @@ int gamd_md_step_host(gamd_ctx* ctx, double* h_x, double* h_v, double* h_f, cons
                       int64_t n_atoms, int32_t n_frames, const double h_box[3], float cutoff,
                       const float* h_feat, double dt);
 
+/* ---- thermostats and rigid-water constraints of the integrator hook ------------------------------------- */
+/* Nose-Hoover chain state (the globals xi{i}, vxi{i}, G{i}, Q{i}, scale, KE2, bathKE, bathPE of
+ * code/hack_integrator.py:249-261).  Lives in DEVICE memory: either inside the ctx (gamd_md_configure, used by
+ * gamd_md_run) or in a caller-owned device buffer of sizeof(gamd_nhc_state) bytes (one per Hack*Integrator object,
+ * so that copy_state_from_integrator is a device-to-device copy).  gamd_nhc_get_state / _set_state move it to / from
+ * the host (synchronous). */
+#define GAMD_NHC_MAX 16
+typedef struct {
+  int32_t M, n_c, n_ys, pad_;    /* chain_length (<= GAMD_NHC_MAX), num_mts, num_yoshidasuzuki (1, 3, 5) */
+  double kT, ndf, Qbase;         /* kJ/mol; degrees of freedom; Q = kT / frequency^2 (Q0 = ndf * Q, Q_i = Q) */
+  double xi[GAMD_NHC_MAX], vxi[GAMD_NHC_MAX], G[GAMD_NHC_MAX], Q[GAMD_NHC_MAX];
+  double scale, ke2_in, ke2, bathKE, bathPE;   /* last velocity scale; sum m v^2 before / after it; bath energies */
+} gamd_nhc_state;
+
+enum { GAMD_THERMO_NONE = 0, GAMD_THERMO_NHC = 1, GAMD_THERMO_LANGEVIN = 2 };
+typedef struct {
+  int32_t thermostat;            /* GAMD_THERMO_* */
+  int32_t chain_length, num_mts, num_ys;   /* NHC: hack_integrator.py:191-192 defaults 5, 5, 5 */
+  double kT;                     /* kJ/mol */
+  double frequency;              /* NHC collision_frequency, 1/ps */
+  double ndf;                    /* degrees of freedom; <= 0: 3 n_atoms (minus 3 per rigid molecule) */
+  double friction;               /* Langevin collision_rate, 1/ps */
+  uint64_t seed;                 /* Philox key of the Langevin / Andersen variates */
+  int32_t rigid_water;           /* 1: atoms are [O,H,H] triplets held rigid (constrained=True) */
+  int32_t pad_;
+  double d_oh, d_hh;             /* nm; <= 0: TIP3P 0.09572 / 0.15139 */
+} gamd_md_options;
+
+/* replaces: the constructors of HackNoseHooverIntegrator / HackHalfNoseHooverIntegrator / HackLangevinIntegrator
+ * (code/hack_integrator.py:190-277, 344-425, 93-165) for the device-resident loop: afterwards gamd_md_run runs that
+ * thermostat's two half-step programs (and ConstrainPositions / ConstrainVelocities when rigid_water) instead of
+ * plain velocity Verlet.  Resets the chain (xi = vxi = 0, G = -frequency^2) and the variate counter. */
+int gamd_md_configure(gamd_ctx* ctx, const gamd_md_options* opt);
+/* replaces: propagateNHC (code/hack_integrator.py:289-316 / :454-481): KE2 = sum m v^2, chain, v *= scale;
+ * bath != 0 also evaluates computeEnergies (:483-493).  d_state NULL = the ctx's own chain. */
+int gamd_nhc_init_state(gamd_ctx* ctx, gamd_nhc_state* d_state, int32_t chain_length, int32_t num_mts, int32_t num_ys,
+                        double kT, double frequency, double ndf, void* stream);
+int gamd_nhc_propagate(gamd_ctx* ctx, gamd_nhc_state* d_state, double* d_v, const double* d_mass, int64_t n_atoms,
+                       double dt, int32_t bath, void* stream);
+int gamd_nhc_get_state(gamd_ctx* ctx, const gamd_nhc_state* d_state, gamd_nhc_state* h_out, void* stream);
+int gamd_nhc_set_state(gamd_ctx* ctx, gamd_nhc_state* d_state, const gamd_nhc_state* h_in, void* stream);
+/* replaces: HackLangevinIntegrator step body (code/hack_integrator.py:141-165), no constraints:
+ * v += dt/2 f/m; x += dt/2 v; v = a v + b sqrt(kT/m) gaussian; x += dt/2 v.
+ * d_gaussian fp64 [n,3] standard normals, or NULL: Philox4x32-10 keyed by (seed, step counter, atom). */
+int gamd_langevin_first_half(gamd_ctx* ctx, double* d_x, double* d_v, const double* d_f, const double* d_mass,
+                             int64_t n_atoms, double dt, double kT, double friction, const double* d_gaussian,
+                             void* stream);
+/* replaces: the collision stage of HackAndersenVVIntegrator (code/hack_integrator.py:66-68), per DOF:
+ * collision = step(p_collision - uniform); v = (1 - collision) v + collision sqrt(kT/m) gaussian.
+ * d_uniform / d_gaussian fp64 [n,3] or both NULL (Philox). */
+int gamd_andersen_collide(gamd_ctx* ctx, double* d_v, const double* d_mass, int64_t n_atoms, double kT,
+                          double p_collision, const double* d_uniform, const double* d_gaussian, void* stream);
+/* replaces: OpenMM ConstrainPositions / ConstrainVelocities for rigid 3-site water (addConstrainPositions /
+ * addConstrainVelocities, code/hack_integrator.py:84-86, 146-165, 274-277, 421-422): analytic SETTLE.
+ * Atoms are [O,H,H] triplets.  d_x0: positions that satisfy the constraints (start of the step); d_x: the
+ * unconstrained new positions, constrained in place; d_v (may be NULL): v += (x_constrained - x)/dt_corr. */
+int gamd_settle_positions(gamd_ctx* ctx, const double* d_x0, double* d_x, double* d_v, const double* d_mass,
+                          int64_t n_mol, double dt_corr, double d_oh, double d_hh, void* stream);
+int gamd_settle_velocities(gamd_ctx* ctx, const double* d_x, double* d_v, const double* d_mass, int64_t n_mol,
+                           void* stream);
+
 /* ---- TIP4P virtual sites ------------------------------------------------------------------------ */
 /* replaces: the M-site strip of WaterDataNew (code/train_utils.py:58-64: the model sees rows with
  * arange % 4 < 3 of a 4-site water box [O,H,H,M]) and OpenMM's average3 virtual-site placement of the

@@ -11,6 +11,9 @@ properties (reversibility, harmonic-oscillator energy, equipartition).
   vv_second_half   HackHalfVelocityIntegrator :171-178 / HackHalfNoseHooverIntegrator :419-425
   nhc_propagate    propagateNHC :289-316 (Yoshida-Suzuki n_ys in {1,3,5}, n_c multi-steps)
   langevin_first_half  HackLangevinIntegrator :141-165 (B, A/2, O, A/2)
+  andersen_collide     HackAndersenVVIntegrator :66-68 (per-DOF collisions)
+  bath_energies        computeEnergies :483-493
+  run_nvt_nhc          the NVT driver loop of test_nosehoover.py:100-118 with both half-step programs
 """
 import numpy as np
 
@@ -93,3 +96,42 @@ def langevin_first_half(x, v, f_last, m, dt, kT, gamma, gaussian):
     v = a * v + b * sigma * gaussian
     x = x + (dt / 2) * v
     return x, v
+
+
+def andersen_collide(v, m, kT, p_collision, uniform, gaussian):
+    """``collision = step(p_collision - uniform); v = (1-collision)*v + collision*sigma_v*gaussian`` per DOF
+    (hack_integrator.py:66-68; OpenMM ``step(x)`` is 0 for x < 0 and 1 otherwise)."""
+    coll = (p_collision - uniform >= 0).astype(np.float64)
+    sigma_v = np.sqrt(kT / m)[:, None]
+    return (1 - coll) * v + coll * sigma_v * gaussian
+
+
+def bath_energies(st):
+    """computeEnergies (hack_integrator.py:483-493): (bathKE, bathPE)."""
+    ke = float(np.sum(0.5 * st.Q * st.vxi ** 2))
+    pe = st.kT * (st.ndf * st.xi[0] + float(np.sum(st.xi[1:]))) if st.M else 0.0
+    return ke, pe
+
+
+def run_nvt_nhc(force_fn, x, v, m, dt, n_steps, st, n_c=5, n_ys=5, constrain=None):
+    """NVT driver loop (test_nosehoover.py:100-118): first half = propagateNHC, kick, drift [, constrain];
+    forces; second half = kick [, constrain v], propagateNHC.  ``force_fn(x_nm) -> F``; ``constrain`` is an optional
+    pair (positions(x0, x1) -> x1c, velocities(x, v) -> vc).  Returns x, v, f, KE trace."""
+    x, v = np.array(x, dtype=np.float64), np.array(v, dtype=np.float64)
+    f = force_fn(x)
+    ke = []
+    for _ in range(n_steps):
+        v = nhc_propagate(st, v, m, dt, n_c, n_ys)
+        x0 = x
+        x, v = vv_first_half(x, v, f, m, dt)
+        if constrain is not None:
+            xc = constrain[0](x0, x)
+            v = v + (xc - x) / dt
+            x = xc
+        f = force_fn(x)
+        v = vv_second_half(v, f, m, dt)
+        if constrain is not None:
+            v = constrain[1](x, v)
+        v = nhc_propagate(st, v, m, dt, n_c, n_ys)
+        ke.append(kinetic_energy(v, m))
+    return x, v, f, np.array(ke)

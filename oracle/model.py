@@ -135,10 +135,12 @@ def forward(sd, kind, pos_lst, edge_lst, box, x=None, bond=None, return_intermed
         h = sd["node_emb"].repeat((off, 1))
     else:
         h = _lin(sd, "node_encoder", torch.as_tensor(x, dtype=torch.float32))
-    inter = dict(e=e, h=[h])
+    inter = dict(e=e, h=[h], agg=[], hn=[])
     for l in range(n_conv_layers(sd)):
-        h = mp_layer(sd, l, h, e, center, neigh)
+        h, parts = mp_layer(sd, l, h, e, center, neigh, return_parts=True)
         inter["h"].append(h)
+        inter["agg"].append(parts["agg"])
+        inter["hn"].append(parts["hn"])
     out = decode(sd, h)
     if return_intermediates:
         return out, inter

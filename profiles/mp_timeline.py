@@ -10,9 +10,9 @@ eng = MDEngine("lj", random_state_dict(0, kind="lj"), L, 7.5, m, 0.0, 1010.0, pr
 eng.set_state(pos / 10.0, maxwell_boltzmann(m, 100.0, 1))
 eng.set_state(pos / 10.0, maxwell_boltzmann(m, 100.0, 1))
 torch.cuda.synchronize()
-t = eng.ctx.debug_tensor("dbg", torch.int64, (16, 256)).cpu().numpy()
+t = eng.ctx.debug_tensor("dbg", torch.int64, (24, 256)).cpu().numpy()
 np.save('/root/repo/gpurun_out/timeline.npy', t)
-for w in (0, 4, 8, 12):
+for w in (0, 4, 8, 12, 16, 20):
     r = t[w]
     base = r[0]
     # per tile: 14 records: [tile start, after stage0 A arrive, (wait_start, wait_end, epi_end) x 4]

@@ -19,6 +19,8 @@ from oracle import md as omd  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10000)
 ap.add_argument("--system", default="lj", choices=["lj", "tip3p"])
+ap.add_argument("--dt", type=float, default=None, help="ps; tip3p default 0.001 (round-1 fixture), 0.002 writes "
+                "nve_tip3p774_dt2fs_oracle_ke.npy (SURVEY 8d C2: dt = 2 fs)")
 a = ap.parse_args()
 fix = os.path.join(ROOT, "tests", "golden", "fixtures")
 if a.system == "tip3p":
@@ -34,8 +36,10 @@ if a.system == "tip3p":
     feat[::3] = 1.0
     ff = omd.OracleForceField(sd, "water", 20.0, 4.2, s["mean"], s["var"], bond=water_bonds(258),
                               feat=torch.from_numpy(feat))
-    _, _, _, trace = omd.run_nve(ff, pos / 10.0, v0, m, 0.001, a.steps)
-    np.save(os.path.join(ROOT, "tests", "golden", "nve_tip3p774_oracle_ke.npy"), trace[:, 1].astype(np.float64))
+    dt = a.dt or 0.001
+    _, _, _, trace = omd.run_nve(ff, pos / 10.0, v0, m, dt, a.steps)
+    name = "nve_tip3p774_oracle_ke.npy" if abs(dt - 0.001) < 1e-12 else "nve_tip3p774_dt%dfs_oracle_ke.npy" % round(dt * 1000)
+    np.save(os.path.join(ROOT, "tests", "golden", name), trace[:, 1].astype(np.float64))
     print("saved", trace.shape, trace[0, 1], trace[-1, 1])
     raise SystemExit(0)
 pos = np.load(os.path.join(fix, "lj_init_pos.npy")).astype(np.float64)

@@ -12,7 +12,7 @@ import torch
 from gamd_b200 import _capi
 from gamd_b200.engine import synthetic_lj_box
 from oracle import md as omd
-from helpers import FIX, make_ctx, rel_err
+from helpers import FIX, check_forces, make_ctx, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -28,9 +28,7 @@ def test_tc_lj258_matches_oracle(prec, tol):
     want = ff.predict_forces(pos)
     got = ctx.compute_forces(torch.as_tensor(pos, device=DEV), 27.27, 7.5).cpu().numpy()
     ctx.check_async_errors()
-    e1, e2 = rel_err(got, want)
-    print("prec", prec, "lj258 rel-to-max", e1, "rel-to-rms", e2)
-    assert e1 <= tol
+    check_forces("tc:lj258", got, want, prec)
     ctx.close()
 
 
@@ -48,9 +46,7 @@ def test_tc_water774_matches_oracle(prec, tol):
     got = ctx.compute_forces(torch.as_tensor(pos, device=DEV), 20.0, 4.2,
                              feat=torch.as_tensor(feat.reshape(-1), device=DEV)).cpu().numpy()
     ctx.check_async_errors()
-    e1, e2 = rel_err(got, want)
-    print("prec", prec, "water774 rel-to-max", e1, "rel-to-rms", e2)
-    assert e1 <= tol
+    check_forces("tc:tip3p774", got, want, prec)
     ctx.close()
 
 
@@ -66,9 +62,7 @@ def test_tc_many_tiles_matches_fp32_path(prec, tol):
     got2 = b.compute_forces(torch.as_tensor(pos, device=DEV), L, 7.5).cpu().numpy()
     b.check_async_errors()
     assert np.array_equal(got, got2), "tensor-core path must be run-to-run deterministic"
-    e1, e2 = rel_err(got, ref)
-    print("prec", prec, "lj27k vs fp32 path rel-to-max", e1, "rel-to-rms", e2)
-    assert e1 <= tol
+    check_forces("tc:lj27k_vs_fp32_path", got, ref, prec)
     b.close()
 
 
@@ -111,7 +105,8 @@ def test_tip4p_virtual_sites():
     ff = omd.OracleForceField(sd, "water", L, 4.2, s["mean"], s["var"], bond=water_bonds(n_mol), feat=feat)
     want = ff.predict_forces(x4[keep])
     f4 = eng.f4.cpu().numpy()
-    assert rel_err(f4[keep], want)[0] <= 1e-4 and np.all(f4[~keep] == 0.0)
+    check_forces("tc:tip4p512", f4[keep], want, "bf16x3")
+    assert np.all(f4[~keep] == 0.0)
     xo, vo, fo, _ = omd.run_nve(ff, x4[keep] / 10.0, v3, m3, 0.002, 3)
     eng.step(3, 0.002)
     eng.eng.ctx.check_async_errors()
