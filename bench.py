@@ -77,6 +77,35 @@ def build_system(name, seed=42):
     return pos, L, 7.5, np.full(len(pos), 39.9), "scaler_lj.npz", "lj", 100.0
 
 
+def kernel_source_hash(files):
+    """sha256 over the CUDA sources a kernel is built from: profiles/traffic_r*.json records it beside the ncu DRAM
+    traffic so that a stale figure is never reported for a changed kernel."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(ROOT, "gamd_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+MP_KERNELS = {   # GAMD_MP_VARIANT -> (kernel name, sources)
+    0: ("k_mp_edge_tc", ["mp_tc.cu", "tc_common.cuh"]),
+    3: ("k_mp_edge_tc3", ["mp_tc3.cu", "tc_common.cuh"]), 4: ("k_mp_edge_tc3", ["mp_tc3.cu", "tc_common.cuh"]),
+    5: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]), 6: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]),
+}
+
+
+def measured_traffic(workload, precision, kernel, sources):
+    """ncu dram__bytes_read + write per launch of `kernel`, or None when no capture exists for exactly this source."""
+    tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if not os.path.exists(tpath):
+        return None
+    rec = json.load(open(tpath)).get(f"{workload}:{precision}:{kernel}")
+    if not rec or rec.get("source_sha16") != kernel_source_hash(sources):
+        return None
+    return rec.get("dram_bytes_per_launch")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -206,6 +235,8 @@ def run_ours(args):
     prec = {"fp32": _capi.PREC_FP32, "bf16x3": _capi.PREC_BF16X3, "bf16": _capi.PREC_BF16}[args.precision]
 
     s_np = None
+    dd_check = None
+    ensemble = None
     mode = args.parallel
     if mode == "auto":
         mode = "dd" if (world > 1 and WORKLOADS[args.workload]["n_side"]) else "replicas"
@@ -232,6 +263,29 @@ def run_ours(args):
         ctx.check_async_errors()
         n = int(md.x.shape[0])
         n_edges = ctx.neighbor_count()
+        if world > 1 and not args.no_dd_check:
+            # correctness of the NCCL data plane on THIS node: forces of the initial configuration, assembled by
+            # global atom id from all ranks, against one single-domain evaluation of the whole box on rank 0
+            f_all = md.gather_by_gid(md.f, n_total)
+            if rank == 0:
+                ctx1 = _capi.Context(kind=_capi.MODEL_LJ, precision=prec, device=local)
+                ctx1.load_state_dict(random_state_dict(0, kind=kind))
+                ctx1.set_scaler(s_np["mean"], s_np["var"])
+                ctx1.finalize()
+                ctx1.reserve(n_total, int(n_total * 34))
+                f_one = ctx1.compute_forces(torch.as_tensor(pos, dtype=torch.float64, device=f"cuda:{local}"), box, rc)
+                ctx1.check_async_errors()
+                d = float((f_all - f_one).abs().max())
+                fmax = float(f_one.abs().max())
+                frms = float((f_one - f_one.mean(0)).pow(2).mean().sqrt())
+                dd_check = {"what": "forces of the initial configuration: slab decomposition over %d ranks (NCCL halo "
+                                    "exchange per layer) vs ONE single-domain evaluation of the whole box on rank 0" % world,
+                            "atoms": n_total, "err_over_max_F": d / fmax, "err_over_rms_F": d / frms, "tol_over_max_F": 1e-4,
+                            "ok": bool(d / fmax <= 1e-4)}
+                ctx1.close()
+                del ctx1, f_one
+            del f_all
+            torch.cuda.empty_cache()
 
         def run_steps(k):
             for _ in range(k):
@@ -298,7 +352,9 @@ def run_ours(args):
         def step_host(bufs):
             eng.step_host(bufs[0].numpy(), bufs[1].numpy(), bufs[2].numpy(), DT)
         atoms_all = world * n
-        scaling = "weak"
+        # the LJ boxes are the domain-decomposition (fixed total work) workloads: their N = 1 line is the base of a
+        # STRONG-scaling series; replicas of a fixed per-GPU system are weak scaling
+        scaling = "strong" if (WORKLOADS[args.workload]["n_side"] and args.parallel != "replicas") else "weak"
         api = "MDEngine.step_host -> gamd_md_step_host (pinned host buffers)"
 
     def barrier():
@@ -342,10 +398,50 @@ def run_ours(args):
     h2d = 3 * n * 24 + (n * 8 + (n * 4 if kind == "water" else 0) if mode != "dd" else 0)
     d2h = 3 * n * 24
 
+    # the host<->device copies of the end-to-end arm on their own (same pinned buffers, same sizes)
+    dbuf = [torch.empty_like(b, device="cuda") for b in bufs]
+    c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    c0.record()
+    for b, d in zip(bufs, dbuf):
+        d.copy_(b, non_blocking=True)
+    c1.record()
+    for b, d in zip(bufs, dbuf):
+        b.copy_(d, non_blocking=True)
+    c2.record()
+    torch.cuda.synchronize()
+    copy_ms = (c0.elapsed_time(c1), c1.elapsed_time(c2))
+    del dbuf
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
+
+    # BASELINE configs[4] on the record of the multi-GPU line: every rank steps 1024 independent LJ-258 replicas
+    # (block-diagonal batch, no collective on the data path); aggregate over the ranks, max-over-ranks time
+    if world > 1 and mode == "dd" and args.workload == "lj1m" and not args.no_ensemble:
+        del md
+        ctx.close()
+        torch.cuda.empty_cache()
+        e_pos, e_box, e_rc, e_m, e_scaler, e_kind, e_temp = build_system("lj258x1024", seed=42 + rank)
+        e_s = np.load(os.path.join(FIX, e_scaler))
+        e_eng = MDEngine(e_kind, random_state_dict(0, kind=e_kind), e_box, e_rc, e_m, e_s["mean"], e_s["var"],
+                         precision=prec, device=local, n_frames=1024)
+        e_eng.set_state(e_pos / 10.0, maxwell_boltzmann(e_m, e_temp, 1234 + rank))
+        e_eng.step(3, DT)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        e_eng.step(10, DT)
+        g1.record()
+        barrier()
+        te = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ensemble = {"workload": "lj258x1024 per GPU (%d replicas over %d GPUs)" % (1024 * world, world),
+                    "value": world * len(e_pos) * 10 / (float(te[0]) * 1e-3), "unit": "atom-steps/s",
+                    "ms_per_step": float(te[0]) / 10, "steps": 10, "scaling": "weak", "parallelism": "independent replicas"}
+        e_eng.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,10 +452,26 @@ def run_ours(args):
     mp_avg_s = mp_ms / max(mp_cnt, 1) * 1e-3
     flop_per_launch = 131072.0 * n_edges            # 4 x (128x128) mat-vec per edge
     achieved = flop_per_launch / mp_avg_s / 1e12 if mp_avg_s > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath) and world == 1:
-        traffic = json.load(open(tpath)).get(f"{args.workload}:{args.precision}:k_mp_edge_tc")
+    mp_variant = int(os.environ.get("GAMD_MP_VARIANT", "6"))
+    mp_kernel, mp_sources = MP_KERNELS.get(mp_variant, MP_KERNELS[6]) if args.precision != "fp32" else ("k_mp_edge", ["model_fp32.cu"])
+    traffic = measured_traffic(args.workload, args.precision, mp_kernel, mp_sources) if world == 1 else None
+    # the other stages against their own bound: encoder 76 800 FLOP / 516 B per edge, neighbor search
+    # 60 N + 4 E bytes, node update 163 840 FLOP per node and layer (+ 33 536 decoder)
+    def _avg(st):
+        ms_, cnt_ = stages[st]
+        return (ms_ / max(cnt_, 1)) * 1e-3
+    enc_s, nbr_s, node_s = _avg("edge_encode"), _avg("neighbor"), _avg("node_update")
+    other_rooflines = []
+    if enc_s > 0:
+        other_rooflines.append({"kernel": "k_edge_encode_tc" if args.precision != "fp32" else "k_edge_encode", "bound": "tensor",
+                                "achieved": 76800.0 * n_edges / enc_s / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                                "frac": 76800.0 * n_edges / enc_s / 1e12 / tensor_peak,
+                                "hbm_frac": 516.0 * n_edges / enc_s / 1e9 / hbm_peak, "ms": enc_s * 1e3})
+    if nbr_s > 0:
+        other_rooflines.append({"kernel": "neighbor search (bin, sort, sweep, scan, fill)", "bound": "hbm",
+                                "achieved": (60.0 * n + 4.0 * n_edges) / nbr_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": (60.0 * n + 4.0 * n_edges) / nbr_s / 1e9 / hbm_peak, "ms": nbr_s * 1e3,
+                                "note": "latency / ALU bound: ~146 exact fp32 predicate evaluations per atom"})
     value = atoms_all * args.steps / (ms * 1e-3)
     e2e_val = atoms_all * e2e_steps / (e2e_ms * 1e-3)
     line = {
@@ -380,8 +492,7 @@ def run_ours(args):
         "edges_per_s_per_layer": n_edges / mp_avg_s if mp_avg_s > 0 else None,
         "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
         "roofline": {"bound": "tensor",
-                     "kernel": ("k_mp_edge_tc" if args.precision != "fp32" else "k_mp_edge") +
-                               " (message-passing edge chain + segmented reduce)",
+                     "kernel": mp_kernel + " (message-passing edge chain + segmented reduce)",
                      # algorithmic FLOPs: 4 x (128x128) mat-vec per edge = 131072; the bf16x3 mode
                      # issues 3x that many tensor-core FLOPs (hardware_tflops) to reach fp32-grade accuracy
                      "achieved": achieved, "peak": tensor_peak / 1.0, "unit": "TFLOP/s",
@@ -390,10 +501,16 @@ def run_ours(args):
                      "hardware_tflops": achieved * (3 if args.precision == "bf16x3" else 1),
                      "hbm_frac": ((516.0 * n_edges + 1028.0 * n) / mp_avg_s / 1e9 / hbm_peak) if mp_avg_s > 0 else None},
         "e2e": {"value": e2e_val, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": api},
+                "steps": e2e_steps, "api": api, "ms_per_step": e2e_ms / e2e_steps,
+                "copies_alone_ms": {"h2d_3_state_arrays": copy_ms[0], "d2h_3_state_arrays": copy_ms[1]}},
+        "roofline_other_stages": other_rooflines,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if dd_check is not None:
+        line["dd_check"] = dd_check
+    if ensemble is not None:
+        line["ensemble"] = ensemble
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = "lj32k" if args.workload == "lj1m" else args.workload
@@ -418,6 +535,8 @@ def main():
                     help="arithmetic of the edge-sized GEMMs: bf16x3 = tcgen05 3-pass split-bf16 (meets the 1e-4 force "
                          "tolerance, default), bf16 = single pass (tolerance 1e-2), fp32 = CUDA-core FFMA parity anchor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dd-check", action="store_true", help="N > 1: skip the single-domain force check on rank 0")
+    ap.add_argument("--no-ensemble", action="store_true", help="N > 1: skip the replica-ensemble sub-record")
     ap.add_argument("--parallel", default="auto", choices=["auto", "dd", "replicas"],
                     help="N > 1: dd = slab domain decomposition of ONE box (strong scaling, default for the LJ boxes), "
                          "replicas = one independent system per rank (weak scaling)")

@@ -581,7 +581,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
             dbg_rec[dbg_n++] = g * 4 + s;
             dbg_rec[dbg_n++] = gtime();
           }
-          const uint32_t bhi = wbase + (uint32_t)(s * 2) * WPART, blo = bhi + WPART;
+          const uint32_t bhi = wbase + (uint32_t)(s * 2) * WPART;      // [hi | lo] images of stage s, WPART apart
           const uint32_t d = tb + floating * 128u, ab = tb + home[g] * 128u;
           if (leader) {       // read by the slot's epilogue threads (both CTAs) after the commit arrives
             sm.home[g] = floating;
@@ -589,16 +589,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
             fence_acq_rel_cluster();
           }
           __syncwarp();
-          const int passes = a.exact ? 3 : 1;
-          uint32_t accum = 0;
-          for (int p = 0; p < passes; p++) {
-            const uint32_t bb = (p == 2) ? blo : bhi;
-            const uint32_t aa = ab + ((p == 1) ? 8u : 0u);
+          // 24 (bf16x3) or 8 (bf16) MMAs, fully unrolled: per MMA only the TMEM column of A and the start-address field
+          // of the B descriptor change, both by compile-time constants
+          {
+            const uint64_t dsc = umma_desc_sw128(bhi);
+            const uint32_t dhi = (uint32_t)(dsc >> 32), dlo_hi = (uint32_t)dsc, dlo_lo = dlo_hi + (WPART >> 4);
 #pragma unroll
-            for (int ks = 0; ks < 8; ks++) {
-              umma_ts2_elect(d, aa + ks * 16, umma_desc_sw128(bb + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, accum,
-                             leader);
-              accum = 1;
+            for (int ks = 0; ks < 8; ks++)     // A_hi * B_hi
+              umma_ts2_elect_lh(d, ab + ks * 16, dlo_hi + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, ks ? 1u : 0u, leader);
+            if (a.exact) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ks++)   // A_lo * B_hi
+                umma_ts2_elect_lh(d, ab + 8 + ks * 16, dlo_hi + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, 1u, leader);
+#pragma unroll
+              for (int ks = 0; ks < 8; ks++)   // A_hi * B_lo
+                umma_ts2_elect_lh(d, ab + ks * 16, dlo_lo + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, 1u, leader);
             }
           }
           if (leader) umma_commit2_mc(&sm.d_ready[g], (uint16_t)3);

@@ -235,6 +235,18 @@ __device__ __forceinline__ void umma_ts2_elect(uint32_t d_tmem, uint32_t a_tmem,
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum), "r"(leader)
       : "memory");
 }
+// the same with the shared-memory descriptor given as two 32-bit halves: inside one GEMM only the low word (start
+// address field) changes, by compile-time constants - the issue loop then costs an add and two register-to-uniform
+// moves per MMA instead of rebuilding the descriptor (measured: 92 -> see profiles/experiments cycles per MMA)
+__device__ __forceinline__ void umma_ts2_elect_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
+                                                  uint32_t idesc, uint32_t accum, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 dsc;\n\tsetp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "mov.b64 dsc, {%2, %3};\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], dsc, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accum), "r"(leader)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on the barrier at this shared-memory offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
