@@ -253,12 +253,15 @@ def run_ours(args):
         # atoms are handed to the neighbouring slab every 4th step; the halo is 0.5 A wider so that an owner can keep
         # integrating a stray atom exactly in between (thermal drift over 4 steps is < 0.1 A; checked at every migration)
         plan = SlabPlan(box, rc, world, rank, margin=DD_MARGIN if world > 1 else 0.0)
-        n_loc_cap = int((n_total / world) * (1.0 + 2.0 * plan.halo / plan.width) * 1.15) + 4096
+        # fixed-size halo messages (unused slots padded): no per-step host synchronisation between migrations
+        halo_cap = (int(1.3 * (n_total / world) * plan.halo / plan.width) + 2048) if world > 1 else None
+        n_loc_cap = int((n_total / world) * 1.15) + 2 * (halo_cap or 0) + 4096
         ctx.reserve(n_loc_cap, int(n_total / world * 1.1 + 4096) * 34)
         md = SlabDomainMD.scatter_global(CudaBackend(ctx, box, rc, 4, overlap=os.environ.get("GAMD_DD_OVERLAP", "0") == "1"),
                                          plan, pos / 10.0,
                                          maxwell_boltzmann(m, temp, 1234), m, f"cuda:{local}",
-                                         migrate_every=DD_MIGRATE_EVERY if world > 1 else 1)
+                                         migrate_every=DD_MIGRATE_EVERY if world > 1 else 1,
+                                         halo_cap=None if os.environ.get("GAMD_DD_EXACT_HALO") == "1" else halo_cap)
         md.compute_forces()
         ctx.check_async_errors()
         n = int(md.x.shape[0])
@@ -483,7 +486,8 @@ def run_ours(args):
         "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "atoms_per_gpu": n,
                    "edges_per_gpu": n_edges, "model": "MDNet 128/128/128 x4 layers, random-init (numpy PCG64 seed 0)",
                    "parallelism": ("slab domain decomposition x%d, NCCL halo exchange per MP layer, atom hand-over "
-                                   "every %d steps (halo margin %.1f A)" % (world, DD_MIGRATE_EVERY, DD_MARGIN)
+                                   "every %d steps (halo margin %.1f A), fixed-capacity halo messages (no host sync "
+                                   "between hand-overs)" % (world, DD_MIGRATE_EVERY, DD_MARGIN)
                                    if mode == "dd" and world > 1 else "slab domain decomposition x1" if mode == "dd"
                                    else ("independent replicas x%d" % world if world > 1 else "single")),
                    "atoms_total": atoms_all, "precision": args.precision,

@@ -168,14 +168,23 @@ class CudaBackend:
     def finish(self, f_own, v_own, mass_own, dt):
         self.ctx.dd_finish(f_own, v_own, mass_own, dt)
 
+    def vv_first(self, x, v, f, mass, dt):
+        """first half-kick + drift of the owned atoms in one kernel (hack_integrator.py:273-274)."""
+        self.ctx.vv_first_half(x, v, f, mass, dt)
+
 
 class SlabDomainMD:
     """Domain-decomposed MD state of one rank.  x in nm, v in nm/ps, f in kJ/mol/nm, masses in Da."""
 
-    def __init__(self, backend, plan, x_nm, v, mass, gid, feat=None, migrate_every=1):
+    def __init__(self, backend, plan, x_nm, v, mass, gid, feat=None, migrate_every=1, halo_cap=None):
         """``migrate_every`` > 1 hands atoms over only every that many steps; in between an owner keeps integrating
         atoms that have left its slab, which is exact as long as none strays further than ``plan.margin`` (checked
-        at every migration; the halo is that much wider)."""
+        at every migration; the halo is that much wider).
+
+        ``halo_cap`` (atoms per face, the same on every rank) makes the steps BETWEEN migrations free of host
+        synchronisation: halo messages have a fixed size, unused slots carry NaN positions (a NaN never passes the
+        neighbor predicate, so a padded slot has no edges and its feature rows are never read), the true counts stay on
+        the device and are checked against the capacity at the next migration."""
         if int(migrate_every) > 1 and plan.margin <= 0.0:
             raise ValueError("migrate_every > 1 needs a SlabPlan with margin > 0")
         self.be, self.plan = backend, plan
@@ -184,10 +193,12 @@ class SlabDomainMD:
         self.n_halo = (0, 0)
         self.migrate_every = int(migrate_every)
         self._since_migration = 0
+        self.halo_cap = None if halo_cap is None or plan.world == 1 else int(halo_cap)
+        self._halo_max = torch.zeros(2, dtype=torch.int64, device=x_nm.device)
 
     # ---- construction ------------------------------------------------------------------------------
     @staticmethod
-    def scatter_global(backend, plan, x_nm_all, v_all, mass_all, device, feat_all=None, migrate_every=1):
+    def scatter_global(backend, plan, x_nm_all, v_all, mass_all, device, feat_all=None, migrate_every=1, halo_cap=None):
         """every rank holds the same global arrays (numpy) and keeps the atoms of its slab."""
         xw = np.mod(x_nm_all[:, 0] * 10.0, plan.box[0])
         own = np.clip(np.floor(xw / plan.width).astype(np.int64), 0, plan.world - 1) == plan.rank
@@ -196,7 +207,7 @@ class SlabDomainMD:
         return SlabDomainMD(backend, plan, t(x_nm_all[own], torch.float64), t(v_all[own], torch.float64),
                             t(mass_all[own], torch.float64), t(gid, torch.int64),
                             None if feat_all is None else t(feat_all[own], torch.float32),
-                            migrate_every=migrate_every)
+                            migrate_every=migrate_every, halo_cap=halo_cap)
 
     # ---- one step ------------------------------------------------------------------------------------
     def migrate(self):
@@ -213,8 +224,12 @@ class SlabDomainMD:
         stray = dx.abs() - half
         far = stray >= p.width                                    # beyond the adjacent slab
         over = stray > p.margin + 1e-9 if self.migrate_every > 1 else torch.zeros_like(far)
-        mine = torch.stack([go_l.sum(), go_r.sum(), far.sum(), over.sum()])
+        mine = torch.stack([go_l.sum(), go_r.sum(), far.sum(), over.sum(), self._halo_max.max()])
         table = _gather_stats(mine, p)
+        if self.halo_cap is not None and int(table[:, 4].max()) > self.halo_cap:
+            raise RuntimeError(f"halo capacity exceeded: {int(table[:, 4].max())} atoms within the cutoff of a slab face, "
+                               f"capacity {self.halo_cap}; forces since the previous migration are incomplete")
+        self._halo_max.zero_()
         if int(table[:, 2].sum()):
             raise RuntimeError("an atom moved further than one slab between two migrations")
         if int(table[:, 3].sum()):
@@ -244,6 +259,8 @@ class SlabDomainMD:
         second half-kick is fused into the read-out."""
         p, be = self.plan, self.be
         pos = self.x * 10.0
+        if self.halo_cap is not None:
+            return self._compute_forces_fixed_cap(pos, dt_kick)
         if p.world > 1:
             to_l, to_r = p.halo_masks_centered(p.centered(pos[:, 0]))
             if p.world == 2:
@@ -281,6 +298,43 @@ class SlabDomainMD:
         else:
             be.finish(self.f, self.v, self.mass, dt_kick)
 
+    def _compute_forces_fixed_cap(self, pos, dt_kick):
+        """the same step with fixed-size halo messages: no host synchronisation anywhere."""
+        p, be, cap = self.plan, self.be, self.halo_cap
+        to_l, to_r = p.halo_masks_centered(p.centered(pos[:, 0]))
+        if p.world == 2:
+            to_r = to_r & ~to_l
+        self._halo_max = torch.maximum(self._halo_max, torch.stack([to_l.sum(), to_r.sum()]))
+        idx_l = torch.nonzero_static(to_l, size=cap, fill_value=-1).flatten()
+        idx_r = torch.nonzero_static(to_r, size=cap, fill_value=-1).flatten()
+        cols = [pos] if self.feat is None else [pos, self.feat[:, None].to(torch.float64)]
+        rows = torch.cat(cols, dim=1)
+        pad = torch.full((1, rows.shape[1]), float("nan"), dtype=rows.dtype, device=rows.device)
+        if self.feat is not None:
+            pad[0, 3] = -1.0                       # the feature column of an unused slot (never read by an edge)
+
+        def take(idx):
+            return torch.where((idx >= 0)[:, None], rows[idx.clamp(min=0)], pad)
+
+        h_l, h_r = _exchange(take(idx_l), take(idx_r), p, cap, cap)
+        self.n_halo = (cap, cap)
+        local = torch.cat([rows, h_l, h_r])
+        pos_local = local[:, 0:3].contiguous()
+        feat_local = None if self.feat is None else local[:, 3].float().contiguous()
+        n_own = pos.shape[0]
+        be.begin(pos_local, n_own, feat_local)
+        i_l, i_r = idx_l.clamp(min=0).to(torch.int32), idx_r.clamp(min=0).to(torch.int32)
+        for l in range(be.n_layers):
+            be.layer(l)
+            if l + 1 < be.n_layers:
+                r_l, r_r = _exchange(be.pack(i_l), be.pack(i_r), p, cap, cap)
+                be.unpack(n_own, r_l)
+                be.unpack(n_own + cap, r_r)
+        if dt_kick is None:
+            be.finish(self.f, None, None, 0.0)
+        else:
+            be.finish(self.f, self.v, self.mass, dt_kick)
+
     def _layers_overlapped(self, idx_l, idx_r, fl, fr, n_own):
         """the message-passing layers with the halo exchange hidden: the rows a layer's node update produced are
         packed, sent and unpacked on a side stream while the main stream already runs the next layer's edge chain on
@@ -309,8 +363,11 @@ class SlabDomainMD:
 
     def step(self, dt):
         """first half-kick + drift, migration, halo exchange + forces, second half-kick."""
-        self.v += (0.5 * dt) * self.f / self.mass[:, None]
-        self.x += dt * self.v
+        if hasattr(self.be, "vv_first"):
+            self.be.vv_first(self.x, self.v, self.f, self.mass, dt)
+        else:
+            self.v += (0.5 * dt) * self.f / self.mass[:, None]
+            self.x += dt * self.v
         self._since_migration += 1
         if self._since_migration >= self.migrate_every:
             self.migrate()

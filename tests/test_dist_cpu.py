@@ -39,7 +39,9 @@ class FakeBackend:
 
     def begin(self, pos_local, n_own, feat_local):
         self.pos, self.n_own, self.gid = pos_local.numpy(), n_own, feat_local.numpy().round().astype(np.int64)
-        assert len(np.unique(self.gid)) == len(self.gid), "an atom reached this rank twice (duplicated halo row)"
+        real = self.gid >= 0                                       # fixed-capacity halo: unused slots carry gid -1, NaN
+        assert np.isnan(self.pos[~real]).all()
+        assert len(np.unique(self.gid[real])) == real.sum(), "an atom reached this rank twice (duplicated halo row)"
         self.rows = np.full((len(self.pos), 4), -1.0, np.float32)
         self.rows[:, 0], self.rows[:, 1] = self.gid, 0            # layer-0 input is position independent
         p = onb.wrap_f32(self.pos.astype(np.float32), self.box)
@@ -47,7 +49,8 @@ class FakeBackend:
         self.edges = e[:, e[0] < n_own]
 
     def layer(self, l):
-        assert np.array_equal(self.rows[:, 0], self.gid) and np.all(self.rows[:, 1] == l), "stale halo rows"
+        real = self.gid >= 0
+        assert np.array_equal(self.rows[real, 0], self.gid[real]) and np.all(self.rows[real, 1] == l), "stale halo rows"
         self.rows[:self.n_own, 1] = l + 1                          # owners advance; halo rows must be refreshed
 
     def pack(self, idx):
@@ -183,6 +186,52 @@ def test_lazy_migration_keeps_neighbourhoods_complete(world):
     ret = mgr.dict()
     mp.spawn(_worker_lazy, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert len(ret) == world and sum(ret.values()) > 0
+
+
+def _worker_fixed_cap(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.Generator(np.random.PCG64(17))
+        n = 500
+        x = rng.uniform(0, BOX, (n, 3)) / 10.0
+        v = rng.standard_normal((n, 3)) * 0.3
+        m = np.full(n, 39.9)
+        plan = SlabPlan(BOX, RC, world, rank, margin=1.5)
+        md = SlabDomainMD.scatter_global(FakeBackend(), plan, x, v, m, "cpu", feat_all=np.arange(n, dtype=np.float32),
+                                         migrate_every=3, halo_cap=260)
+        md.compute_forces()
+        for step in range(6):
+            md.step(0.02)
+            x_all = md.gather_by_gid(md.x, n).numpy() * 10.0
+            ref = onb.edges_jaxmd(x_all, BOX, RC)
+            mine = np.isin(ref[0], md.gid.numpy())
+            assert np.array_equal(onb.edge_set(md.be.local_edges_gid), onb.edge_set(ref[:, mine])), f"step {step}"
+            assert md.n_halo == (260, 260)
+        ret[rank] = md.kinetic_energy()
+        # a capacity that is too small is reported at the next migration, not silently ignored
+        md2 = SlabDomainMD.scatter_global(FakeBackend(), plan, x, v, m, "cpu", feat_all=np.arange(n, dtype=np.float32),
+                                          migrate_every=2, halo_cap=8)
+        md2.compute_forces()
+        try:
+            md2.step(0.001)
+            md2.step(0.001)
+            ret[f"overflow{rank}"] = False
+        except RuntimeError as e:
+            ret[f"overflow{rank}"] = "halo capacity exceeded" in str(e)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fixed_capacity_halo_needs_no_counts(world):
+    """halo messages of a fixed size (unused slots = NaN positions): between migrations no count crosses to the
+    host; the local edge sets equal the single-domain ones and an undersized capacity raises at the next migration."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_fixed_cap, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(set(round(ret[r], 9) for r in range(world))) == 1
+    assert all(ret[f"overflow{r}"] for r in range(world))
 
 
 def test_lazy_migration_needs_margin():

@@ -30,7 +30,7 @@ def _system():
     return pos, L, m, maxwell_boltzmann(m, 100.0, 77)
 
 
-def _worker(rank, world, port, precision, ret, migrate_every=1, margin=0.0, overlap=False):
+def _worker(rank, world, port, precision, ret, migrate_every=1, margin=0.0, overlap=False, halo_cap=None):
     from gamd_b200 import _capi
     from gamd_b200.dist import CudaBackend, SlabDomainMD, SlabPlan
     from gamd_b200.weights import random_state_dict
@@ -47,10 +47,10 @@ def _worker(rank, world, port, precision, ret, migrate_every=1, margin=0.0, over
         ctx.load_state_dict(random_state_dict(1, 5.2, 1.5, kind="lj"))
         ctx.set_scaler(0.0, 1010.0)
         ctx.finalize()
-        ctx.reserve(n, n * 40)
+        ctx.reserve(n + 2 * (halo_cap or 0), n * 40)
         plan = SlabPlan(L, 7.5, world, rank, margin=margin)
         md = SlabDomainMD.scatter_global(CudaBackend(ctx, L, 7.5, 4, overlap=overlap), plan, pos / 10.0, v0, m, f"cuda:{dev}",
-                                         migrate_every=migrate_every)
+                                         migrate_every=migrate_every, halo_cap=halo_cap)
         md.compute_forces()
         ctx.check_async_errors()
         f0 = md.gather_by_gid(md.f, n).cpu().numpy()
@@ -120,6 +120,20 @@ def test_slab_md_split_layers_equals_single_domain():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(3, _free_port(), _capi.PREC_BF16X3, ret, 1, 0.0, True), nprocs=3, join=True)
+    assert np.abs(ret["f0"] - f_ref).max() / np.abs(f_ref).max() <= 1e-4
+    assert np.abs(ret["x5"] - x_ref).max() <= 1e-7
+    assert abs(ret["ke"] - ke_ref) / ke_ref <= 1e-6
+
+
+def test_slab_md_fixed_capacity_halo_equals_single_domain():
+    """world 3, lazy hand-over, FIXED-size halo messages (1500 slots per face, unused ones NaN-padded): the steps
+    between hand-overs run without any host synchronisation and give the same trajectory as one domain."""
+    from gamd_b200 import _capi
+    f_ref, x_ref, ke_ref = _reference(_capi.PREC_BF16X3)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(3, _free_port(), _capi.PREC_BF16X3, ret, 3, 0.3, False, 1500), nprocs=3, join=True)
+    assert ret["halo"] == (1500, 1500)
     assert np.abs(ret["f0"] - f_ref).max() / np.abs(f_ref).max() <= 1e-4
     assert np.abs(ret["x5"] - x_ref).max() <= 1e-7
     assert abs(ret["ke"] - ke_ref) / ke_ref <= 1e-6
