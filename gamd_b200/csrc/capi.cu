@@ -116,6 +116,15 @@ void carve(gamd_ctx* ctx, Carver& c, int64_t A, int64_t E) {
   ctx->stage_c = c.take<double>((size_t)A * 3);
   ctx->stage_m = c.take<double>(A);
   ctx->stage_feat = c.take<float>(A);
+  // Verlet-skin candidate rows: (rc + skin)^3 / rc^3 = 1.59 x the edges for skin = rc / 6, rows padded to 32
+  ctx->vl_cap = 2 * E + 32 * A;
+  ctx->vl_ptr = c.take<int>(A + 1);
+  ctx->vl_cnt = c.take<int>(A + 1);
+  ctx->vl_cand = c.take<int>(ctx->vl_cap);
+  ctx->vl_mask = c.take<uint32_t>(ctx->vl_cap / 32 + 4);
+  ctx->vl_pos_ref = c.take<float4>(A);
+  ctx->vl_flag = c.take<int>(4);
+  ctx->vl_counters = c.take<unsigned long long>(2);
 }
 
 __global__ void k_pack_pos_feat(const float* __restrict__ pos, const float* __restrict__ feat, int64_t n,
@@ -156,8 +165,14 @@ int positions_to_forces(gamd_ctx* ctx, const double* d_x, double scale, int64_t 
   if (rc) return rc;
   if ((rc = nbr_setup_params(ctx, n, n_frames, boxf, cutoff, GAMD_NBR_LT | GAMD_NBR_SELF, &p))) return rc;
   prof_mark(ctx, "neighbor", st);
-  if ((rc = nbr_bin_f64(ctx, d_x, scale, box, p, st))) return rc;
-  if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
+  if (ctx->vl_skin_frac > 0.f && n >= ctx->vl_min_atoms && ctx->vl_cap < (int64_t(1) << 31)) {
+    // candidate list with a skin, rebuilt only when an atom moved more than 0.45 skin (graph_utils.py:21-25)
+    if ((rc = nbr_step_verlet(ctx, d_x, scale, box, p, d_feat, st))) return rc;
+  } else {
+    if ((rc = nbr_bin_f64(ctx, d_x, scale, box, p, st))) return rc;
+    if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
+    ctx->vl_key = 0;          // the cell order changed under the saved candidate rows
+  }
   prof_mark(ctx, "neighbor", st);
   return model_forward(ctx, ctx->pos_feat_s, nullptr, ctx->perm, n, p.atoms_per_frame, boxf, st);
 }
@@ -252,6 +267,9 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   // message-passing edge kernel: 6 = CTA pairs (cta_group::2), resident weights, three tiles in flight (default);
   // 5 = the same with a commit wait between GEMMs; 3 / 4 = three tiles, single CTA; 0 = the round-1 two-tile kernel
   ctx->mp_variant = getenv("GAMD_MP_VARIANT") ? atoi(getenv("GAMD_MP_VARIANT")) : 6;
+  // neighbor candidate reuse: skin as a fraction of the cutoff (reference: 1/6); GAMD_NBR_SKIN=0 rebuilds every step
+  ctx->vl_skin_frac = getenv("GAMD_NBR_SKIN") ? (float)atof(getenv("GAMD_NBR_SKIN")) : (1.f / 6.f);
+  if (getenv("GAMD_NBR_SKIN_MIN_ATOMS")) ctx->vl_min_atoms = atoll(getenv("GAMD_NBR_SKIN_MIN_ATOMS"));
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (ctx->sm_count < 2 && ctx->mp_variant >= 5) ctx->mp_variant = 0;
@@ -319,6 +337,8 @@ int gamd_reserve(gamd_ctx* ctx, int64_t max_atoms, int64_t max_edges) {
   }
   ctx->last_nbr = NbrParams{};
   ctx->graph_key = 0;
+  ctx->vl_key = 0;
+  GAMD_CUDA(cudaMemset(ctx->vl_counters, 0, 2 * sizeof(unsigned long long)));
   return 0;
 }
 
@@ -627,6 +647,12 @@ int gamd_check_async_errors(gamd_ctx* ctx, void* stream) {
   if (flag[0] & 2) {
     ctx->err = "edge list must be sorted by centre with ids in [0, n_atoms)";
     return GAMD_EINVAL;
+  }
+  if (flag[0] & 4) {
+    ctx->vl_key = 0;
+    ctx->err = "neighbor candidate capacity exceeded (" + std::to_string(ctx->vl_cap) + " slots): call gamd_reserve with a "
+               "larger max_edges";
+    return GAMD_ECAPACITY;
   }
   return 0;
 }
@@ -1175,6 +1201,17 @@ int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_byt
 }
 
 int64_t gamd_launch_count(const gamd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gamd_neighbor_stats(gamd_ctx* ctx, int64_t* n_rebuilds, int64_t* n_searches, void* stream) {
+  if (!ctx || !ctx->arena) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  unsigned long long h[2] = {0, 0};
+  GAMD_CUDA(cudaMemcpyAsync(h, ctx->vl_counters, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GAMD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (n_rebuilds) *n_rebuilds = (int64_t)h[0];
+  if (n_searches) *n_searches = (int64_t)h[1];
+  return 0;
+}
 
 int gamd_profile_enable(gamd_ctx* ctx, int32_t on) {
   if (!ctx) return GAMD_EINVAL;

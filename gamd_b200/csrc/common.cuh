@@ -86,6 +86,15 @@ struct gamd_ctx {
   float *agg = nullptr, *part = nullptr, *pred = nullptr;
   int* inv_perm = nullptr;                                    // caller index -> sorted index (domain decomposition)
   float* feat_s = nullptr;                                    // node type feature in sorted order
+  // Verlet-skin reuse of the candidate list (neighbor.cu: nbr_step_verlet)
+  float vl_skin_frac = 0.f;               // skin = vl_skin_frac * cutoff (the reference: dr_threshold = cutoff / 6); 0 = off
+  int64_t vl_min_atoms = 20000;           // smaller systems rebuild every step (launch-bound: the gated pipeline costs more)
+  int64_t vl_cap = 0;                     // candidate capacity
+  int *vl_ptr = nullptr, *vl_cnt = nullptr, *vl_cand = nullptr, *vl_flag = nullptr;
+  uint32_t* vl_mask = nullptr;
+  float4* vl_pos_ref = nullptr;
+  unsigned long long* vl_counters = nullptr;   // [rebuilds, steps]
+  uint64_t vl_key = 0, vl_epoch = 0;
   // export helpers
   int *deg_o = nullptr, *row_ptr_o = nullptr;
   // host staging
@@ -170,6 +179,8 @@ int nbr_setup_params(gamd_ctx* ctx, int64_t n_atoms, int n_frames, const float b
 int nbr_bin_f32(gamd_ctx* ctx, const float* d_pos, const NbrParams& p, cudaStream_t st);
 int nbr_bin_f64(gamd_ctx* ctx, const double* d_pos_or_x, double scale, const double* box64, const NbrParams& p, cudaStream_t st);
 int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, cudaStream_t st);
+int nbr_step_verlet(gamd_ctx* ctx, const double* d_x, double scale, const double* box64, const NbrParams& p,
+                    const float* d_feat, cudaStream_t st);
 int nbr_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float* d_dist, float* d_norm, cudaStream_t st);
 int csr_from_sorted_coo(gamd_ctx* ctx, const int64_t* d_center, const int64_t* d_neigh, int64_t n_atoms, int64_t n_edges, cudaStream_t st);
 int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cudaStream_t st);

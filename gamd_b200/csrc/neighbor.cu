@@ -14,6 +14,7 @@
 // The predicate is evaluated for every DIRECTED pair from its own centre, one IEEE rounding
 // per operation (no FMA contraction), so the edge set is bit-identical to oracle/neighbor.py.
 #include "common.cuh"
+#include <cstring>
 
 // ------------------------------------------------------------------------------------------
 // arithmetic shared by bin / sweep / export
@@ -81,9 +82,9 @@ __global__ void k_bin_f32(const float* __restrict__ pos, NbrParams p, float4* __
 //   feature positions   = f32(np.mod(pos, L)) in float64 first  (train_network_lj.py:141-142)
 __global__ void k_bin_f64(const double* __restrict__ x, double scale, double bx, double by, double bz,
                           NbrParams p, float4* __restrict__ pos_nbr, float4* __restrict__ pos_feat,
-                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, const int* __restrict__ gate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_atoms) return;
+  if (i >= p.n_atoms || (gate && !*gate)) return;
   double px = x[3 * i] * scale, py = x[3 * i + 1] * scale, pz = x[3 * i + 2] * scale;
   float wx = wrap_pos((float)px, p.box[0]), wy = wrap_pos((float)py, p.box[1]), wz = wrap_pos((float)pz, p.box[2]);
   double fx = fmod(px, bx), fy = fmod(py, by), fz = fmod(pz, bz);
@@ -132,8 +133,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
   return res;
 }
 
-__global__ void k_scan_partial(const int* __restrict__ in, int64_t n, int* __restrict__ block_sums) {
+__global__ void k_scan_partial(const int* __restrict__ in, int64_t n, int* __restrict__ block_sums,
+                               const int* __restrict__ gate) {
   __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+  if (gate && !*gate) return;
   int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int s = 0;
 #pragma unroll
@@ -144,8 +147,9 @@ __global__ void k_scan_partial(const int* __restrict__ in, int64_t n, int* __res
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-__global__ void k_scan_top(int* __restrict__ block_sums, int nb) {
+__global__ void k_scan_top(int* __restrict__ block_sums, int nb, const int* __restrict__ gate) {
   __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+  if (gate && !*gate) return;
   int carry = 0;
   for (int base = 0; base < nb; base += SCAN_THREADS) {
     int i = base + threadIdx.x;
@@ -158,8 +162,10 @@ __global__ void k_scan_top(int* __restrict__ block_sums, int nb) {
 }
 
 __global__ void k_scan_final(const int* __restrict__ in, int* __restrict__ out, int64_t n,
-                             const int* __restrict__ block_sums, int* __restrict__ total_out) {
+                             const int* __restrict__ block_sums, int* __restrict__ total_out,
+                             const int* __restrict__ gate) {
   __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+  if (gate && !*gate) return;
   int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
@@ -181,24 +187,26 @@ __global__ void k_scan_final(const int* __restrict__ in, int* __restrict__ out, 
   }
 }
 
-__global__ void k_scan_empty(int* out, int* total_out) {
+__global__ void k_scan_empty(int* out, int* total_out, const int* gate) {
+  if (gate && !*gate) return;
   out[0] = 0;
   if (total_out) *total_out = 0;
 }
 
-static int scan_with_total(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, int* d_total, cudaStream_t st) {
+static int scan_with_total(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, int* d_total, cudaStream_t st,
+                           const int* gate = nullptr) {
   if (n == 0) {
-    k_scan_empty<<<1, 1, 0, st>>>(d_out, d_total);
+    k_scan_empty<<<1, 1, 0, st>>>(d_out, d_total, gate);
     GAMD_LAUNCH_CHECK();
     return 0;
   }
   int nb = ceil_div(n, SCAN_TILE);
   int* sums = (int*)ctx->scan_tmp;
-  k_scan_partial<<<nb, SCAN_THREADS, 0, st>>>(d_in, n, sums);
+  k_scan_partial<<<nb, SCAN_THREADS, 0, st>>>(d_in, n, sums, gate);
   GAMD_LAUNCH_CHECK();
-  k_scan_top<<<1, SCAN_THREADS, 0, st>>>(sums, nb);
+  k_scan_top<<<1, SCAN_THREADS, 0, st>>>(sums, nb, gate);
   GAMD_LAUNCH_CHECK();
-  k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(d_in, d_out, n, sums, d_total);
+  k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(d_in, d_out, n, sums, d_total, gate);
   GAMD_LAUNCH_CHECK();
   return 0;
 }
@@ -216,8 +224,9 @@ int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cu
 #define RS_WARPS (RS_THREADS / 32)
 
 __global__ void k_radix_hist(const uint32_t* __restrict__ keys, int n, int shift, int nblocks,
-                             uint32_t* __restrict__ hist) {
+                             uint32_t* __restrict__ hist, const int* __restrict__ gate) {
   __shared__ uint32_t s_h[256];
+  if (gate && !*gate) return;
   s_h[threadIdx.x] = 0;
   __syncthreads();
   int base = blockIdx.x * RS_TILE;
@@ -232,9 +241,11 @@ __global__ void k_radix_hist(const uint32_t* __restrict__ keys, int n, int shift
 
 __global__ void k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
                                 int shift, int nblocks, const uint32_t* __restrict__ offs,
-                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                const int* __restrict__ gate) {
   // warp w owns the contiguous sub-range [w*256, (w+1)*256) of the tile -> stable
   __shared__ uint32_t s_cnt[RS_WARPS][256];
+  if (gate && !*gate) return;
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int d = lane; d < 256; d += 32) s_cnt[w][d] = 0;
   __syncwarp();
@@ -281,18 +292,19 @@ __global__ void k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_
 }
 
 // sorts ctx->keys[0]/vals[0]; returns the index (0/1) of the buffer holding the result
-static int radix_sort_pairs(gamd_ctx* ctx, int n, int key_bits, cudaStream_t st, int* result_buf) {
+static int radix_sort_pairs(gamd_ctx* ctx, int n, int key_bits, cudaStream_t st, int* result_buf,
+                            const int* gate = nullptr) {
   int cur = 0;
   int nblocks = ceil_div(n, RS_TILE);
   for (int shift = 0; shift < key_bits; shift += 8) {
-    k_radix_hist<<<nblocks, RS_THREADS, 0, st>>>(ctx->keys[cur], n, shift, nblocks, ctx->radix_hist);
+    k_radix_hist<<<nblocks, RS_THREADS, 0, st>>>(ctx->keys[cur], n, shift, nblocks, ctx->radix_hist, gate);
     GAMD_LAUNCH_CHECK();
-    int rc = exclusive_scan_i32(ctx, (const int*)ctx->radix_hist, (int*)ctx->radix_hist + 256 * nblocks + 8,
-                                (int64_t)256 * nblocks, st);
+    int rc = scan_with_total(ctx, (const int*)ctx->radix_hist, (int*)ctx->radix_hist + 256 * nblocks + 8,
+                             (int64_t)256 * nblocks, nullptr, st, gate);
     if (rc) return rc;
     k_radix_scatter<<<nblocks, RS_THREADS, 0, st>>>(ctx->keys[cur], ctx->vals[cur], n, shift, nblocks,
                                                     ctx->radix_hist + 256 * nblocks + 8, ctx->keys[cur ^ 1],
-                                                    ctx->vals[cur ^ 1]);
+                                                    ctx->vals[cur ^ 1], gate);
     GAMD_LAUNCH_CHECK();
     cur ^= 1;
   }
@@ -307,9 +319,10 @@ __global__ void k_gather_sorted(const uint32_t* __restrict__ keys, const uint32_
                                 int ncells, const float4* __restrict__ pos_nbr, const float4* __restrict__ pos_feat,
                                 const float* __restrict__ feat, float4* __restrict__ pos_nbr_s,
                                 float4* __restrict__ pos_feat_s, int* __restrict__ perm,
-                                int* __restrict__ inv_perm, int* __restrict__ cell_start) {
+                                int* __restrict__ inv_perm, int* __restrict__ cell_start,
+                                const int* __restrict__ gate) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
+  if (s >= n || (gate && !*gate)) return;
   int i = (int)vals[s];
   pos_nbr_s[s] = pos_nbr[i];
   float4 pf = pos_feat[i];
@@ -345,7 +358,7 @@ __device__ __forceinline__ int sweep_range(int lo, int hi, int s, const float4& 
       int dst = base + cnt + __popc(m & ((1u << lane) - 1u));
       if (dst < cap) {
         col[dst] = j;
-        edst[dst] = s;
+        if (edst) edst[dst] = s;
       }
     }
     cnt += __popc(m);
@@ -358,10 +371,11 @@ __global__ void __launch_bounds__(256) k_sweep(NbrParams p, const float4* __rest
                                                const uint32_t* __restrict__ keys,
                                                const int* __restrict__ cell_start, int* __restrict__ deg,
                                                const int* __restrict__ row_ptr, int* __restrict__ col,
-                                               int* __restrict__ edst, int cap, int* __restrict__ err_flag) {
+                                               int* __restrict__ edst, int cap, int* __restrict__ err_flag,
+                                               const int* __restrict__ gate) {
   int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
-  if (s >= p.n_atoms) return;
+  if (s >= p.n_atoms || (gate && !*gate)) return;
   float4 pc = pos[s];
   int key = (int)keys[s];
   int frame = key / p.cells_per_frame;
@@ -473,7 +487,7 @@ int nbr_bin_f32(gamd_ctx* ctx, const float* d_pos, const NbrParams& p, cudaStrea
 int nbr_bin_f64(gamd_ctx* ctx, const double* d_x, double scale, const double* box64, const NbrParams& p,
                 cudaStream_t st) {
   k_bin_f64<<<ceil_div(p.n_atoms, 256), 256, 0, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, ctx->pos_nbr,
-                                                      ctx->pos_feat, ctx->keys[0], ctx->vals[0]);
+                                                      ctx->pos_feat, ctx->keys[0], ctx->vals[0], nullptr);
   GAMD_LAUNCH_CHECK();
   return 0;
 }
@@ -502,17 +516,17 @@ int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, c
   }
   k_gather_sorted<<<ceil_div(n, 256), 256, 0, st>>>(ctx->keys[buf], ctx->vals[buf], n, (int)ncells, ctx->pos_nbr,
                                                     ctx->pos_feat, d_feat, ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm,
-                                                    ctx->inv_perm, ctx->cell_start);
+                                                    ctx->inv_perm, ctx->cell_start, nullptr);
   GAMD_LAUNCH_CHECK();
   int cap = (int)ctx->cap_edges;
   int blocks = ceil_div((int64_t)n * 32, 256);
   bool general = (p.flags & GAMD_NBR_NOWRAP) != 0;
   if (general)
     k_sweep<false, true><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg, nullptr,
-                                                 nullptr, nullptr, cap, ctx->err_flag);
+                                                 nullptr, nullptr, cap, ctx->err_flag, nullptr);
   else
     k_sweep<false, false><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg,
-                                                  nullptr, nullptr, nullptr, cap, ctx->err_flag);
+                                                  nullptr, nullptr, nullptr, cap, ctx->err_flag, nullptr);
   GAMD_LAUNCH_CHECK();
   rc = scan_with_total(ctx, ctx->deg, ctx->row_ptr, n, ctx->n_edges, st);
   if (rc) return rc;
@@ -520,10 +534,193 @@ int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, c
   GAMD_LAUNCH_CHECK();
   if (general)
     k_sweep<true, true><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg,
-                                                ctx->row_ptr, ctx->col_idx, ctx->edge_dst, cap, ctx->err_flag);
+                                                ctx->row_ptr, ctx->col_idx, ctx->edge_dst, cap, ctx->err_flag, nullptr);
   else
     k_sweep<true, false><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg,
-                                                 ctx->row_ptr, ctx->col_idx, ctx->edge_dst, cap, ctx->err_flag);
+                                                 ctx->row_ptr, ctx->col_idx, ctx->edge_dst, cap, ctx->err_flag, nullptr);
+  GAMD_LAUNCH_CHECK();
+  ctx->last_nbr = p;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Verlet-skin reuse (the reference: jax-md neighbor_list with dr_threshold = cutoff / 6 rebuilds its candidate
+// list only when an atom has moved more than half the skin, and re-applies the exact mask every step,
+// code/graph_utils.py:21-25, :36-44, :51-61).  Same here, without a host round trip:
+//
+//   every step   k_vl_place   positions in the cell order of the LAST rebuild; max displacement since then > 0.45 skin
+//                             -> device flag
+//   flag set     the cell-list pipeline above, gated on the flag (bin, sort, gather) with cells of edge >= rc + skin,
+//                a 27-cell sweep with the predicate dr2 < (rc + skin)^2 -> per-centre candidate rows (padded to 32)
+//   every step   k_vl_count   the EXACT predicate on the ~36 candidates of a centre (instead of ~146 atoms of 27 cells),
+//                             ballot masks kept; scan; k_vl_fill writes the CSR from the masks (one predicate pass)
+//
+// The edge SET is that of the exact predicate on the current wrapped fp32 positions - identical to the rebuilt-every-
+// step path - because every pair within rc now was within rc + skin at the rebuild (each atom moved < skin / 2).
+// ------------------------------------------------------------------------------------------
+__global__ void k_vl_place(const double* __restrict__ x, double scale, double bx, double by, double bz, NbrParams p,
+                           const int* __restrict__ perm, const float* __restrict__ feat, float4* __restrict__ pos_nbr,
+                           float4* __restrict__ pos_nbr_s, float4* __restrict__ pos_feat_s,
+                           const float4* __restrict__ pos_ref, float thr2, int* __restrict__ flag) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.n_atoms || *flag) return;     // a forced rebuild (first use, new system) recomputes everything anyway
+  const int i = perm[s];
+  double px = x[3 * i] * scale, py = x[3 * i + 1] * scale, pz = x[3 * i + 2] * scale;
+  float wx = wrap_pos((float)px, p.box[0]), wy = wrap_pos((float)py, p.box[1]), wz = wrap_pos((float)pz, p.box[2]);
+  double fx = fmod(px, bx), fy = fmod(py, by), fz = fmod(pz, bz);
+  if (fx < 0.0) fx += bx;
+  if (fy < 0.0) fy += by;
+  if (fz < 0.0) fz += bz;
+  pos_nbr_s[s] = make_float4(wx, wy, wz, __int_as_float(i));
+  pos_nbr[i] = make_float4(wx, wy, wz, __int_as_float(i));      // caller order (gamd_neighbor_export distances)
+  pos_feat_s[s] = make_float4((float)fx, (float)fy, (float)fz, feat ? feat[i] : 0.f);
+  const float4 r = pos_ref[s];
+  const float dx = min_image<false>(wx - r.x, p.box[0], p.half[0]);
+  const float dy = min_image<false>(wy - r.y, p.box[1], p.half[1]);
+  const float dz = min_image<false>(wz - r.z, p.box[2], p.half[2]);
+  if (dx * dx + dy * dy + dz * dz > thr2) *flag = 1;      // benign race: every writer stores 1
+}
+
+__global__ void k_vl_pad32(const int* __restrict__ deg, int n, int* __restrict__ cnt32, const int* __restrict__ gate) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n || !*gate) return;
+  cnt32[s] = (deg[s] + 31) & ~31;
+}
+
+// candidate rows: the sweep's output compacted at cand_ptr[s]; the padding slots get -1; reference positions saved
+__global__ void k_vl_finish_rows(const int* __restrict__ deg, const int* __restrict__ cand_ptr, int n, int cap,
+                                 int* __restrict__ cand, const float4* __restrict__ pos_nbr_s,
+                                 float4* __restrict__ pos_ref, int* __restrict__ err_flag, const int* __restrict__ gate) {
+  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= n || !*gate) return;
+  if (lane == 0) pos_ref[s] = pos_nbr_s[s];
+  const int b = cand_ptr[s], e = cand_ptr[s + 1], d = deg[s];
+  if (e > cap) {
+    if (lane == 0) atomicOr(err_flag, 4);
+    return;
+  }
+  for (int k = b + d + lane; k < e; k += 32) cand[k] = -1;
+}
+
+__global__ void k_vl_clear(int* flag, unsigned long long* counters) {
+  counters[1] += 1ull;                 // steps
+  if (*flag) counters[0] += 1ull;      // rebuilds
+  *flag = 0;
+}
+
+__global__ void __launch_bounds__(256) k_vl_count(NbrParams p, const float4* __restrict__ pos,
+                                                  const int* __restrict__ cand_ptr, const int* __restrict__ cand,
+                                                  uint32_t* __restrict__ vmask, int* __restrict__ deg) {
+  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= p.n_atoms) return;
+  const float4 pc = pos[s];
+  if (__float_as_int(pc.w) >= p.n_centers) {
+    if (lane == 0) deg[s] = 0;
+    return;
+  }
+  const int b = cand_ptr[s], e = cand_ptr[s + 1];
+  int cnt = 0;
+  for (int k = b; k < e; k += 32) {
+    const int j = cand[k + lane];
+    bool ok = false;
+    if (j >= 0) {
+      ok = pass_pred(pair_dr2<false>(pc, pos[j], p), p);
+      if (j == s) ok = (p.flags & GAMD_NBR_SELF) != 0;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) vmask[k >> 5] = m;
+    cnt += __popc(m);
+  }
+  if (lane == 0) deg[s] = cnt;
+}
+
+__global__ void __launch_bounds__(256) k_vl_fill(int n, const int* __restrict__ cand_ptr, const int* __restrict__ cand,
+                                                 const uint32_t* __restrict__ vmask, const int* __restrict__ row_ptr,
+                                                 int* __restrict__ col, int* __restrict__ edst, int cap,
+                                                 int* __restrict__ err_flag) {
+  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= n) return;
+  int out = row_ptr[s];
+  if (row_ptr[s + 1] > cap) {
+    if (lane == 0 && row_ptr[s + 1] > row_ptr[s]) atomicOr(err_flag, 1);
+    return;
+  }
+  const int b = cand_ptr[s], e = cand_ptr[s + 1];
+  for (int k = b; k < e; k += 32) {
+    const uint32_t m = vmask[k >> 5];
+    if ((m >> lane) & 1u) {
+      const int dst = out + __popc(m & ((1u << lane) - 1u));
+      col[dst] = cand[k + lane];
+      edst[dst] = s;
+    }
+    out += __popc(m);
+  }
+}
+
+// engine path (fp64 state, wrapped positions, dr2 < rc^2, self pairs kept): positions -> CSR with skin reuse
+int nbr_step_verlet(gamd_ctx* ctx, const double* d_x, double scale, const double* box64, const NbrParams& p,
+                    const float* d_feat, cudaStream_t st) {
+  const int n = p.n_atoms;
+  const float skin = ctx->vl_skin_frac * p.rc;
+  float boxf[3] = {p.box[0], p.box[1], p.box[2]};
+  NbrParams pc;                                   // the candidate search: cells and predicate of radius rc + skin
+  int rc = nbr_setup_params(ctx, n, p.n_frames, boxf, p.rc + skin, p.flags, &pc);
+  if (rc) return rc;
+  pc.n_centers = p.n_centers;
+  // anything that invalidates the saved cell order / candidate rows forces a rebuild
+  uint64_t key = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+  mix((uint64_t)n); mix((uint64_t)p.n_frames); mix((uint64_t)p.flags); mix((uint64_t)ctx->arena); mix((uint64_t)d_feat);
+  for (int d = 0; d < 3; d++) { uint32_t b; memcpy(&b, &p.box[d], 4); mix(b); }
+  { uint32_t b; memcpy(&b, &p.rc, 4); mix(b); }
+  mix(ctx->vl_epoch);
+  int* flag = ctx->vl_flag;
+  if (key != ctx->vl_key) {
+    GAMD_CUDA(cudaMemsetAsync(flag, 0xff, sizeof(int), st));
+    ctx->vl_key = key;
+  }
+  const float thr = 0.45f * skin;
+  k_vl_place<<<ceil_div(n, 256), 256, 0, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, ctx->perm, d_feat,
+                                               ctx->pos_nbr, ctx->pos_nbr_s, ctx->pos_feat_s, ctx->vl_pos_ref, thr * thr, flag);
+  GAMD_LAUNCH_CHECK();
+  // ---- rebuild, gated on the flag ----
+  k_bin_f64<<<ceil_div(n, 256), 256, 0, st>>>(d_x, scale, box64[0], box64[1], box64[2], pc, ctx->pos_nbr, ctx->pos_feat,
+                                              ctx->keys[0], ctx->vals[0], flag);
+  GAMD_LAUNCH_CHECK();
+  const int64_t ncells = (int64_t)pc.cells_per_frame * pc.n_frames;
+  int bits = 1;
+  while (((int64_t)1 << bits) < ncells) bits++;
+  int buf = 0;
+  if (ncells > 1 && (rc = radix_sort_pairs(ctx, n, bits, st, &buf, flag))) return rc;
+  k_gather_sorted<<<ceil_div(n, 256), 256, 0, st>>>(ctx->keys[buf], ctx->vals[buf], n, (int)ncells, ctx->pos_nbr,
+                                                    ctx->pos_feat, d_feat, ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm,
+                                                    ctx->inv_perm, ctx->cell_start, flag);
+  GAMD_LAUNCH_CHECK();
+  const int blocks = ceil_div((int64_t)n * 32, 256);
+  const int cap_c = (int)ctx->vl_cap;
+  k_sweep<false, false><<<blocks, 256, 0, st>>>(pc, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg, nullptr,
+                                                nullptr, nullptr, cap_c, ctx->err_flag, flag);
+  GAMD_LAUNCH_CHECK();
+  k_vl_pad32<<<ceil_div(n, 256), 256, 0, st>>>(ctx->deg, n, ctx->vl_cnt, flag);
+  GAMD_LAUNCH_CHECK();
+  if ((rc = scan_with_total(ctx, ctx->vl_cnt, ctx->vl_ptr, n, nullptr, st, flag))) return rc;
+  k_sweep<true, false><<<blocks, 256, 0, st>>>(pc, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg, ctx->vl_ptr,
+                                               ctx->vl_cand, nullptr, cap_c, ctx->err_flag + 2, flag);
+  GAMD_LAUNCH_CHECK();
+  k_vl_finish_rows<<<blocks, 256, 0, st>>>(ctx->deg, ctx->vl_ptr, n, cap_c, ctx->vl_cand, ctx->pos_nbr_s, ctx->vl_pos_ref,
+                                           ctx->err_flag, flag);
+  GAMD_LAUNCH_CHECK();
+  k_vl_clear<<<1, 1, 0, st>>>(flag, ctx->vl_counters);
+  GAMD_LAUNCH_CHECK();
+  // ---- every step: the exact predicate on the candidates ----
+  k_vl_count<<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->vl_ptr, ctx->vl_cand, ctx->vl_mask, ctx->deg);
+  GAMD_LAUNCH_CHECK();
+  if ((rc = scan_with_total(ctx, ctx->deg, ctx->row_ptr, n, ctx->n_edges, st))) return rc;
+  const int cap = (int)ctx->cap_edges;
+  k_nbr_guard<<<1, 1, 0, st>>>(ctx->row_ptr, n, cap, ctx->n_edges, ctx->err_flag);
+  GAMD_LAUNCH_CHECK();
+  k_vl_fill<<<blocks, 256, 0, st>>>(n, ctx->vl_ptr, ctx->vl_cand, ctx->vl_mask, ctx->row_ptr, ctx->col_idx, ctx->edge_dst,
+                                    cap, ctx->err_flag);
   GAMD_LAUNCH_CHECK();
   ctx->last_nbr = p;
   return 0;

@@ -281,6 +281,10 @@ int gamd_check_async_errors(gamd_ctx* ctx, void* stream);
 /* device pointers into ctx scratch, valid until the next gamd_reserve: names
  * "row_ptr","col_idx","edge_dst","perm","n_edges","pos_sorted","e_emb","h","agg","pred". */
 int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_bytes);
+/* candidate-list reuse of the fused force path (code/graph_utils.py:21-25: jax-md rebuilds its neighbor candidates
+ * only when an atom has moved more than half the skin, dr_threshold = cutoff / 6, and applies the exact mask every
+ * step): number of candidate rebuilds and of searches since gamd_reserve.  Synchronises `stream`. */
+int gamd_neighbor_stats(gamd_ctx* ctx, int64_t* n_rebuilds, int64_t* n_searches, void* stream);
 /* number of kernel launches issued by this ctx since creation */
 int64_t gamd_launch_count(const gamd_ctx* ctx);
 /* per-stage CUDA-event timers on the launching stream.  Stages: "neighbor", "edge_encode",

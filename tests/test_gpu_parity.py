@@ -372,3 +372,31 @@ def test_nve_10k_steps_tip3p774_tracks_oracle_trace():
     assert rel[:1000].max() < 5e-3, rel[:1000].max()
     assert rel.max() < 5e-2, rel.max()
     assert abs(slope - 1.0) < 2e-2
+
+
+def test_neighbor_skin_reuse_keeps_the_edge_set_exact():
+    """the fused force path keeps its neighbor CANDIDATES for as long as no atom has moved more than 0.45 skin
+    (skin = cutoff / 6, code/graph_utils.py:21-25) and applies the exact predicate to them every step: the edge set
+    must stay bit-identical to a from-scratch cell-list search of the same positions, across rebuilds."""
+    from gamd_b200.engine import synthetic_lj_box
+    pos, L = synthetic_lj_box(28)                     # 21,952 atoms: above the skin path's size threshold
+    n = len(pos)
+    a, _ = make_ctx("lj", 0, 5.2, 1.5, max_atoms=n, max_edges=n * 40)          # skin path (compute_forces)
+    b, _ = make_ctx("lj", 0, 5.2, 1.5, max_atoms=n, max_edges=n * 40)          # from-scratch search (neighbor_build)
+    rng = np.random.Generator(np.random.PCG64(31))
+    drift = rng.standard_normal(pos.shape)
+    drift /= np.linalg.norm(drift, axis=1, keepdims=True)
+    steps = 30
+    for t in range(steps):
+        pos = pos + 0.07 * drift + 0.01 * rng.standard_normal(pos.shape)        # ~0.56 A (0.45 skin) every 8 steps
+        a.compute_forces(torch.as_tensor(pos, device=DEV), L, 7.5)
+        a.check_async_errors()
+        ea = a.neighbor_export().cpu().numpy()
+        b.neighbor_build(torch.as_tensor(pos, dtype=torch.float32, device=DEV), L, 7.5)
+        eb = b.neighbor_export().cpu().numpy()
+        assert np.array_equal(ea, eb), f"step {t}: edge sets differ ({ea.shape[1]} vs {eb.shape[1]})"
+    rebuilds, searches = a.neighbor_stats()
+    print("skin reuse: rebuilds", rebuilds, "of", searches, "searches")
+    assert searches == steps and 2 <= rebuilds <= steps // 2
+    a.close()
+    b.close()
