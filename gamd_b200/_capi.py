@@ -67,6 +67,8 @@ SIGNATURES = {
     "gamd_neighbor_export": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gamd_model_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(c_double), c_void_p, c_void_p,
                                      c_int64, c_void_p, c_void_p, c_void_p]),
+    "gamd_dynbox_forward": (c_int32, [c_void_p, c_void_p, c_int64, POINTER(c_double), c_float, c_void_p, c_void_p,
+                                      c_void_p]),
     "gamd_compute_forces": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(c_double), c_float, c_void_p,
                                       c_void_p, c_void_p]),
     "gamd_compute_forces_host": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(c_double), c_float,
@@ -232,6 +234,15 @@ class Context:
         out = torch.empty((n, 3), dtype=torch.float32, device=pos_f32.device)
         self._check(self.lib.gamd_model_forward(self._h, _ptr(pos_f32), n, n_frames, _box3(box), _ptr(center),
                                                 _ptr(neigh), int(center.shape[0]), _ptr(feat), _ptr(out), _stream()))
+        return out
+
+    def dynbox_forward(self, pos_f32, box, cutoff, feat):
+        """WaterMDDynamicBoxNet.forward for one frame: normalised force fp32 [n,3] in the caller's atom order."""
+        import torch
+        n = pos_f32.shape[0]
+        out = torch.empty((n, 3), dtype=torch.float32, device=pos_f32.device)
+        self._check(self.lib.gamd_dynbox_forward(self._h, _ptr(pos_f32), n, _box3(box), float(cutoff), _ptr(feat),
+                                                 _ptr(out), _stream()))
         return out
 
     def compute_forces(self, pos_f64, box, cutoff, feat=None, n_frames=1, out=None):

@@ -712,6 +712,42 @@ int gamd_model_forward(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, int32
   return 0;
 }
 
+__global__ void k_unpermute_pred(const float* __restrict__ pred, const int* __restrict__ perm, int64_t n,
+                                 float* __restrict__ out) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int64_t i = perm[s];
+  out[3 * i] = pred[3 * s];
+  out[3 * i + 1] = pred[3 * s + 1];
+  out[3 * i + 2] = pred[3 * s + 2];
+}
+
+int gamd_dynbox_forward(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, const double h_box[3], float cutoff,
+                        const float* d_feat, float* d_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!d_pos || !h_box || !d_out || !d_feat || n_atoms <= 0) return GAMD_EINVAL;
+  if (ctx->desc.kind != GAMD_MODEL_DYNBOX) {
+    ctx->err = "gamd_dynbox_forward needs a GAMD_MODEL_DYNBOX context";
+    return GAMD_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = check_bonds(ctx, n_atoms, 1))) return rc;
+  float boxf[3] = {(float)h_box[0], (float)h_box[1], (float)h_box[2]};
+  NbrParams p;
+  // md_module.get_neighbor: |d| <= rc, no self pair, positions exactly as given (md_module.py:103-121)
+  if ((rc = nbr_setup_params(ctx, n_atoms, 1, boxf, cutoff, GAMD_NBR_LE | GAMD_NBR_NOWRAP, &p))) return rc;
+  prof_mark(ctx, "neighbor", st);
+  if ((rc = nbr_bin_f32(ctx, d_pos, p, st))) return rc;
+  if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
+  ctx->vl_key = 0;
+  prof_mark(ctx, "neighbor", st);
+  if ((rc = model_forward(ctx, ctx->pos_feat_s, nullptr, ctx->perm, n_atoms, (int)n_atoms, boxf, st))) return rc;
+  k_unpermute_pred<<<ceil_div(n_atoms, 256), 256, 0, st>>>(ctx->pred, ctx->perm, n_atoms, d_out);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
 int gamd_compute_forces(gamd_ctx* ctx, const double* d_pos, int64_t n_atoms, int32_t n_frames, const double h_box[3],
                         float cutoff, const float* d_feat, double* d_force, void* stream) {
   int rc = check_ready(ctx);

@@ -40,6 +40,7 @@ struct EncTcArgs {
   float length_mean, length_std;
   float box[3];
   int n_edge_in, use_bond, expand_edge, atoms_per_frame, exact;
+  int dynbox;     // WaterMDDynamicBoxNet: rel = -(min-image of pos[center] - pos[neigh])  (nn_module.py:327)
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_encode_tc(EncTcArgs a) {
           const float4 pc = a.pos[c], pn = a.pos[n];
           // rel = pos[neigh] - pos[center]; remainder(rel + L/2, L) - L/2   (nn_module.py:615-621)
           float rr[3] = {pn.x - pc.x, pn.y - pc.y, pn.z - pc.z};
+          if (a.dynbox) { rr[0] = pc.x - pn.x; rr[1] = pc.y - pn.y; rr[2] = pc.z - pn.z; }
 #pragma unroll
           for (int d = 0; d < 3; d++) {
             const float half = 0.5f * a.box[d];
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_encode_tc(EncTcArgs a) {
             float m = fmodf(t, a.box[d]);
             if (m < 0.f) m = __fadd_rn(m, a.box[d]);
             rr[d] = __fsub_rn(m, half);
+            if (a.dynbox) rr[d] = -rr[d];
           }
           const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rr[0], rr[0]), __fmul_rn(rr[1], rr[1])), __fmul_rn(rr[2], rr[2])));
           const float den = dist + 1e-8f;
@@ -376,6 +379,7 @@ int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig
   a.expand_edge = mw.expand_edge;
   a.atoms_per_frame = atoms_per_frame;
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
+  a.dynbox = mw.kind == GAMD_MODEL_DYNBOX ? 1 : 0;
   k_edge_encode_tc<<<ctx->sm_count, THREADS, smem, st>>>(a);
   GAMD_LAUNCH_CHECK();
   return 0;

@@ -210,6 +210,7 @@ struct EncArgs {
   float length_mean, length_std;
   int n_edge_in, use_bond, expand_edge;
   float box[3];
+  int dynbox;     // WaterMDDynamicBoxNet: rel = -(min-image of pos[center] - pos[neigh])  (nn_module.py:327, md_module.py:65-66)
 };
 
 __global__ void __launch_bounds__(NT) k_edge_encode(EncArgs a, const float4* __restrict__ pos,
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(NT) k_edge_encode(EncArgs a, const float4* __r
         float4 pc = pos[c], pn = pos[n];
         // rel = pos[neigh] - pos[center]; remainder(rel + L/2, L) - L/2   (nn_module.py:615-621)
         float r[3] = {pn.x - pc.x, pn.y - pc.y, pn.z - pc.z};
+        if (a.dynbox) { r[0] = pc.x - pn.x; r[1] = pc.y - pn.y; r[2] = pc.z - pn.z; }
 #pragma unroll
         for (int d = 0; d < 3; d++) {
           float half = 0.5f * a.box[d];
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(NT) k_edge_encode(EncArgs a, const float4* __r
           float m = fmodf(t, a.box[d]);
           if (m < 0.f) m = __fadd_rn(m, a.box[d]);
           r[d] = __fsub_rn(m, half);
+          if (a.dynbox) r[d] = -r[d];
         }
         float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[0], r[0]), __fmul_rn(r[1], r[1])), __fmul_rn(r[2], r[2])));
         float den = dist + 1e-8f;
@@ -563,7 +566,8 @@ int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64
     if ((rc = edge_encode_tc_launch(ctx, pos_feat, orig_id, atoms_per_frame, box, st))) return rc;
   } else {
     EncArgs ea{mw.enc0_t, mw.enc0_b, mw.enc2_t, mw.enc2_b, mw.enc4_t, mw.enc4_b, mw.eln_w, mw.eln_b, mw.centers,
-               mw.length_mean, mw.length_std, mw.n_edge_in, mw.use_bond, mw.expand_edge, {box[0], box[1], box[2]}};
+               mw.length_mean, mw.length_std, mw.n_edge_in, mw.use_bond, mw.expand_edge, {box[0], box[1], box[2]},
+               mw.kind == GAMD_MODEL_DYNBOX ? 1 : 0};
     k_edge_encode<<<grid_edge, NT, smem, st>>>(ea, pos_feat, ctx->col_idx, ctx->edge_dst, ctx->n_edges, orig_id,
                                                ctx->d_bond, atoms_per_frame, ctx->e_emb, nullptr);
     GAMD_LAUNCH_CHECK();

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .nn_module import SimpleMDNetNew, WaterMDNetNew
+from .nn_module import SimpleMDNetNew, WaterMDDynamicBoxNet, WaterMDNetNew
 
 
 def create_water_bond(total_atom_num):
@@ -121,3 +121,32 @@ class WaterForceFacade(_ForceFacade):
         """code/water/train_network_tip3p.py:142-159; ``feat`` is the [N,1] O=1/H=0 tensor."""
         f = feat.detach().cpu().numpy() if isinstance(feat, torch.Tensor) else np.asarray(feat)
         return self._predict(pos, np.ascontiguousarray(f.reshape(-1), dtype=np.float32))
+
+
+class DynamicBoxForceFacade(_ForceFacade):
+    """``ParticleNetLightning`` of code/water/train_network_real_large.py:106-162: the box is an argument of every
+    call (``predict_forces(feat, pos, box_size)``), the neighbor search runs inside the model."""
+    KIND = "dynbox"
+
+    def __init__(self, args, cutoff, model_weights_ckpt=None, scaler_ckpt=None, precision=_capi.PREC_BF16X3):
+        super().__init__(args, None, cutoff, 0, model_weights_ckpt, scaler_ckpt, precision)
+
+    def build_model(self, args, ckpt=None):
+        model = WaterMDDynamicBoxNet(in_feats=1, encoding_size=args.encoding_size, out_feats=3,
+                                     hidden_dim=args.hidden_dim, edge_embedding_dim=args.edge_embedding_dim,
+                                     conv_layer=args.conv_layer, drop_edge=args.drop_edge,
+                                     use_layer_norm=args.use_layer_norm, update_edge=getattr(args, "update_edge", False),
+                                     expand_edge=getattr(args, "expand_edge", True))
+        if ckpt is not None:
+            model.load_state_dict(torch.load(ckpt, map_location="cpu"))
+        return model
+
+    def predict_forces(self, feat, pos: np.ndarray, box_size):
+        """code/water/train_network_real_large.py:148-162: wrap, model, de-normalise (float64)."""
+        pos = np.mod(np.asarray(pos), box_size)
+        dev = next(self.pnet_model.parameters()).device
+        self.pnet_model.context(precision=self.precision)
+        p = torch.from_numpy(np.ascontiguousarray(pos)).float().to(dev)
+        f = feat.to(dev) if isinstance(feat, torch.Tensor) else torch.as_tensor(np.asarray(feat), device=dev)
+        pred = self.pnet_model([p], f, [box_size], self.cutoff)
+        return self.denormalize(pred.detach().cpu().numpy(), self.training_var, self.training_mean)

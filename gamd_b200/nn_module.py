@@ -241,3 +241,72 @@ class WaterMDNetNew(_MDNetBase):
             self._ctx_dirty = True
         feat = x.float().reshape(-1).contiguous()
         return self._run(fluid_pos_lst, fluid_edge_lst, feat)
+
+
+class WaterMDDynamicBoxNet(_MDNetBase):
+    """Dynamic-box water model (nn_module.py:266-407): the neighbor search runs INSIDE the model for every frame with
+    that frame's (per-axis) box - ``md_module.get_neighbor``: ``|d| <= cutoff``, no self edges, positions as given -
+    and the edge direction is ``-(pos[center] - pos[neigh])`` min-imaged (:327).  ``forward(pos_lst, x, box_size_lst,
+    cutoff)``; one fused library call per frame (``gamd_dynbox_forward``).
+
+    Built for the 128-wide model with LayerNorm and RBF expansion (``update_edge=False``); the 256 / 512 / 768-wide
+    DFT-water configurations of train_network_real_large.py:74-98 raise (GAMD_EUNSUPPORTED)."""
+    _kind = _capi.MODEL_DYNBOX
+
+    def __init__(self, in_feats, encoding_size, out_feats, bond=None, hidden_dim=128, conv_layer=4,
+                 edge_embedding_dim=128, dropout=0.1, drop_edge=True, use_layer_norm=False, update_edge=False,
+                 expand_edge=True):
+        super().__init__()
+        if in_feats != 1:
+            raise NotImplementedError("in_feats must be 1 (O=1 / H=0 feature)")
+        if update_edge:
+            raise NotImplementedError("update_edge=True is not built")
+        if not expand_edge:
+            raise NotImplementedError("expand_edge=False is not built")
+        self.use_bond = bond is not None
+        self._bond = None
+        self._bond_atoms = 0
+        if bond is not None:
+            b = bond.detach().cpu().numpy() if isinstance(bond, torch.Tensor) else np.asarray(bond)
+            self._bond = b.astype(np.int64)
+            self._bond_atoms = int(b.max()) + 1
+        self.expand_edge = expand_edge
+        n_in = 3 + 1 + N_RBF + (1 if self.use_bond else 0)
+        self._init_common(encoding_size, out_feats, None, hidden_dim, conv_layer, edge_embedding_dim, drop_edge,
+                          use_layer_norm, n_in)
+        self.node_encoder = nn.Linear(in_feats, encoding_size)
+        self._finish_init(encoding_size, hidden_dim, n_in)
+
+    def _bonds(self):
+        return self._bond
+
+    @torch.no_grad()
+    def forward(self, fluid_pos_lst: List[torch.Tensor], x: torch.Tensor, box_size_lst, cutoff) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("gamd_b200 models are inference-only: call .eval()")
+        if len(fluid_pos_lst) != len(box_size_lst):
+            raise ValueError("position and box lists differ in length")
+        feat = x.float().reshape(-1).contiguous()
+        outs, off = [], 0
+        for pos, box in zip(fluid_pos_lst, box_size_lst):
+            n = int(pos.shape[0])
+            if self.use_bond and n != self._bond_atoms:
+                self._bond_atoms = n
+                self._ctx_dirty = True
+            b = box.detach().cpu().numpy() if isinstance(box, torch.Tensor) else np.asarray(box, dtype=np.float64)
+            b3 = np.broadcast_to(b.reshape(-1).astype(np.float64), (3,))
+            rho = n / float(np.prod(b3))
+            per_atom = int(1.5 * (4.0 / 3.0 * np.pi * float(cutoff) ** 3 * rho)) + 16
+            ctx = self.context(n, n * per_atom)
+            while True:
+                try:
+                    out = ctx.dynbox_forward(pos.float().contiguous(), b3, float(cutoff), feat[off:off + n].contiguous())
+                    ctx.check_async_errors()
+                    break
+                except _capi.GamdError as e:       # edge buffer overflow: re-allocate and redo the frame
+                    if e.code != _capi.ECAPACITY:
+                        raise
+                    ctx.reserve(ctx.cap_atoms, 2 * ctx.cap_edges)
+            outs.append(out)
+            off += n
+        return torch.cat(outs)

@@ -20,7 +20,8 @@
  *   - one ctx per device and per host thread; distinct ctxs are independent.
  *   - sizes the kernels are built for in this round: encoding_size = hidden_dim =
  *     edge_embedding_dim = 128 (every LJ / TIP3P / TIP4P config the reference ships,
- *     code/LJ/test_script/test_nosehoover.py:66-69); other widths return GAMD_EUNSUPPORTED.
+ *     code/LJ/test_script/test_nosehoover.py:66-69, and the 128-wide dynamic-box model); other widths (the
+ *     256 / 512 / 768 DFT-water models of train_network_real_large.py) return GAMD_EUNSUPPORTED.
  */
 #ifndef GAMD_B200_H
 #define GAMD_B200_H
@@ -134,6 +135,15 @@ int gamd_neighbor_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float*
 int gamd_model_forward(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, int32_t n_frames,
                        const double h_box[3], const int64_t* d_center, const int64_t* d_neigh,
                        int64_t n_edges, const float* d_feat, float* d_out, void* stream);
+
+/* ---- dynamic-box model: neighbor search inside the model ---------------------------------- */
+/* replaces: WaterMDDynamicBoxNet.forward for ONE frame (code/nn_module.py:391-407 -> build_graph :338-365 ->
+ *           md_module.get_neighbor, code/md_module.py:93-126): per-axis box h_box, |d| <= cutoff, no self edges,
+ *           positions exactly as given (the facade wraps them first, code/water/train_network_real_large.py:150),
+ *           edge direction -(min-image of pos[center] - pos[neigh]) (:327).  d_feat fp32 [n] node feature,
+ *           d_out fp32 [n,3] normalised force in the caller's atom order.  Needs a GAMD_MODEL_DYNBOX context. */
+int gamd_dynbox_forward(gamd_ctx* ctx, const float* d_pos, int64_t n_atoms, const double h_box[3], float cutoff,
+                        const float* d_feat, float* d_out, void* stream);
 
 /* ---- stage 1+2 fused: positions -> forces ---------------------------------------------- */
 /* replaces: ParticleNetLightning.predict_forces (code/LJ/train_network_lj.py:133-157,

@@ -400,3 +400,32 @@ def test_neighbor_skin_reuse_keeps_the_edge_set_exact():
     assert searches == steps and 2 <= rebuilds <= steps // 2
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("prec", [_capi.PREC_FP32, _capi.PREC_BF16X3])
+def test_dynamic_box_model_matches_reference_golden(golden_dir, prec):
+    """WaterMDDynamicBoxNet (code/nn_module.py:266-407) through the reference's own call surface
+    ``forward(pos_lst, x, box_size_lst, cutoff)``: per-axis box, |d| <= cutoff, no self edges, sign-flipped edge
+    direction.  Golden = the UNMODIFIED reference module on 192 atoms in a 12.4 x 12.9 x 13.3 A box
+    (tests/golden/make_golden.py: dynbox_case); a second frame with another box checks the per-frame box list."""
+    from gamd_b200.nn_module import WaterMDDynamicBoxNet
+    from gamd_b200.weights import random_state_dict
+    g = np.load(os.path.join(golden_dir, "dynbox192.npz"))
+    model = WaterMDDynamicBoxNet(1, 128, 3, hidden_dim=128, conv_layer=4, edge_embedding_dim=128, drop_edge=False,
+                                 use_layer_norm=True, update_edge=False, expand_edge=True)
+    sd = random_state_dict(int(g["seed"]), 2.9, 0.9, kind="dynbox", use_bond=False)
+    model.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    model.cuda().eval()
+    model.context(precision=prec)
+    pos = torch.as_tensor(g["pos"], device=DEV)
+    x = torch.zeros(192, 1, device=DEV)
+    x[::3] = 1.0
+    out = model([pos], x, [g["box"]], 4.2).cpu().numpy()
+    check_forces("golden:dynbox192", out, g["force"], prec)
+    # two frames, two different boxes: frame 0 must be unchanged, frame 1 must equal the oracle on its own box
+    box2 = np.array([13.0, 12.2, 14.1], dtype=np.float32)
+    pos2 = torch.as_tensor(np.mod(g["pos"] * 1.01, box2).astype(np.float32), device=DEV)
+    out2 = model([pos, pos2], torch.cat([x, x]), [g["box"], box2], 4.2).cpu().numpy()
+    assert np.array_equal(out2[:192], out)
+    want2 = omodel.forward_dynbox(sd, [pos2.cpu().numpy()], x.cpu(), [box2], 4.2).numpy()
+    check_forces("oracle:dynbox192_frame2", out2[192:], want2, prec)
