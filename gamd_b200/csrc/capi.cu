@@ -165,7 +165,10 @@ int positions_to_forces(gamd_ctx* ctx, const double* d_x, double scale, int64_t 
   if (rc) return rc;
   if ((rc = nbr_setup_params(ctx, n, n_frames, boxf, cutoff, GAMD_NBR_LT | GAMD_NBR_SELF, &p))) return rc;
   prof_mark(ctx, "neighbor", st);
-  if (ctx->vl_skin_frac > 0.f && n >= ctx->vl_min_atoms && ctx->vl_cap < (int64_t(1) << 31)) {
+  if (ctx->small_frames && p.atoms_per_frame <= 1024) {
+    // launch-bound systems: the whole search in one CTA per frame (one launch for a single frame)
+    if ((rc = nbr_small_frames(ctx, d_x, scale, box, p, d_feat, st))) return rc;
+  } else if (ctx->vl_skin_frac > 0.f && n >= ctx->vl_min_atoms && ctx->vl_cap < (int64_t(1) << 31)) {
     // candidate list with a skin, rebuilt only when an atom moved more than 0.45 skin (graph_utils.py:21-25)
     if ((rc = nbr_step_verlet(ctx, d_x, scale, box, p, d_feat, st))) return rc;
   } else {
@@ -270,6 +273,7 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   // neighbor candidate reuse: skin as a fraction of the cutoff (reference: 1/6); GAMD_NBR_SKIN=0 rebuilds every step
   ctx->vl_skin_frac = getenv("GAMD_NBR_SKIN") ? (float)atof(getenv("GAMD_NBR_SKIN")) : (1.f / 6.f);
   if (getenv("GAMD_NBR_SKIN_MIN_ATOMS")) ctx->vl_min_atoms = atoll(getenv("GAMD_NBR_SKIN_MIN_ATOMS"));
+  ctx->small_frames = !(getenv("GAMD_NBR_SMALL") && atoi(getenv("GAMD_NBR_SMALL")) == 0);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (ctx->sm_count < 2 && ctx->mp_variant >= 5) ctx->mp_variant = 0;

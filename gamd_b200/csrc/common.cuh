@@ -88,6 +88,7 @@ struct gamd_ctx {
   float* feat_s = nullptr;                                    // node type feature in sorted order
   // Verlet-skin reuse of the candidate list (neighbor.cu: nbr_step_verlet)
   float vl_skin_frac = 0.f;               // skin = vl_skin_frac * cutoff (the reference: dr_threshold = cutoff / 6); 0 = off
+  bool small_frames = true;               // one-CTA-per-frame search for frames of <= 1024 atoms (GAMD_NBR_SMALL=0: off)
   int64_t vl_min_atoms = 20000;           // smaller systems rebuild every step (launch-bound: the gated pipeline costs more)
   int64_t vl_cap = 0;                     // candidate capacity
   int *vl_ptr = nullptr, *vl_cnt = nullptr, *vl_cand = nullptr, *vl_flag = nullptr;
@@ -165,7 +166,7 @@ void prof_mark(gamd_ctx* ctx, const char* stage, cudaStream_t st);   // call bef
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16, GAMD_ATTR_MP_TC2 = 32 };
+enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16, GAMD_ATTR_MP_TC2 = 32, GAMD_ATTR_NBR_SMALL = 64 };
 
 // every stream entry point runs on the context's device, whatever device the calling thread had current
 #define GAMD_ENTER(ctx)                                                                  \
@@ -179,6 +180,8 @@ int nbr_setup_params(gamd_ctx* ctx, int64_t n_atoms, int n_frames, const float b
 int nbr_bin_f32(gamd_ctx* ctx, const float* d_pos, const NbrParams& p, cudaStream_t st);
 int nbr_bin_f64(gamd_ctx* ctx, const double* d_pos_or_x, double scale, const double* box64, const NbrParams& p, cudaStream_t st);
 int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, cudaStream_t st);
+int nbr_small_frames(gamd_ctx* ctx, const double* d_x, double scale, const double* box64, const NbrParams& p,
+                     const float* d_feat, cudaStream_t st);
 int nbr_step_verlet(gamd_ctx* ctx, const double* d_x, double scale, const double* box64, const NbrParams& p,
                     const float* d_feat, cudaStream_t st);
 int nbr_export(gamd_ctx* ctx, int64_t* d_edge_idx, int64_t cap, float* d_dist, float* d_norm, cudaStream_t st);

@@ -544,6 +544,187 @@ int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, c
 }
 
 // ------------------------------------------------------------------------------------------
+// Small frames (<= 1024 atoms per frame: LJ-258, TIP3P-774, the replica ensembles): one CTA per frame does the whole
+// search - wrap, exact predicate on every ordered pair (with 3 cells per axis the 27-cell sweep visits every atom
+// anyway), ballot masks kept in shared memory, block scan, CSR fill.  A single frame needs ONE launch instead of ~20
+// (radix passes, scans, two sweeps); the step of these systems is launch-latency bound.
+// Atoms keep the caller's order (perm = identity); a row lists its neighbours by ascending atom id.
+// ------------------------------------------------------------------------------------------
+#define SMALL_MAX 1024
+#define SMALL_THREADS 1024
+
+struct SmallSmem {
+  int deg[SMALL_MAX + 1];
+  int warp_sums[33];
+  float4 pos[SMALL_MAX];
+};
+
+// FUSED: the frame's row offsets start at 0 and the kernel writes row_ptr / n_edges itself (n_frames == 1);
+// otherwise pass 0 (count: deg + masks to global) and pass 1 (fill from the masks) bracket the global scan
+template <int PASS, bool FUSED>
+__global__ void __launch_bounds__(SMALL_THREADS) k_nbr_small(const double* __restrict__ x, double scale, double bx,
+                                                             double by, double bz, NbrParams p,
+                                                             const float* __restrict__ feat, float4* __restrict__ pos_nbr,
+                                                             float4* __restrict__ pos_nbr_s, float4* __restrict__ pos_feat_s,
+                                                             int* __restrict__ perm, int* __restrict__ inv_perm,
+                                                             int* __restrict__ deg_g, int* __restrict__ row_ptr,
+                                                             uint32_t* __restrict__ gmask, int* __restrict__ col,
+                                                             int* __restrict__ edst, int cap, int* __restrict__ n_edges,
+                                                             int* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned char small_raw[];
+  SmallSmem& sm = *reinterpret_cast<SmallSmem*>(small_raw);
+  uint32_t* smask = reinterpret_cast<uint32_t*>(small_raw + sizeof(SmallSmem));   // FUSED: [n][words] ballot masks
+  const int n = p.atoms_per_frame, words = (n + 31) >> 5;
+  const int base = blockIdx.x * n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  if (PASS == 0) {
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int g = base + i;
+      const double px = x[3 * g] * scale, py = x[3 * g + 1] * scale, pz = x[3 * g + 2] * scale;
+      const float wx = wrap_pos((float)px, p.box[0]), wy = wrap_pos((float)py, p.box[1]), wz = wrap_pos((float)pz, p.box[2]);
+      double fx = fmod(px, bx), fy = fmod(py, by), fz = fmod(pz, bz);
+      if (fx < 0.0) fx += bx;
+      if (fy < 0.0) fy += by;
+      if (fz < 0.0) fz += bz;
+      const float4 pn = make_float4(wx, wy, wz, __int_as_float(g));
+      sm.pos[i] = pn;
+      pos_nbr[g] = pn;
+      pos_nbr_s[g] = pn;
+      pos_feat_s[g] = make_float4((float)fx, (float)fy, (float)fz, feat ? feat[g] : 0.f);
+      perm[g] = g;
+      inv_perm[g] = g;
+    }
+  } else {
+    for (int i = tid; i < n; i += blockDim.x) sm.pos[i] = pos_nbr_s[base + i];
+  }
+  __syncthreads();
+  uint32_t* mask = FUSED ? smask : gmask + (size_t)base * words;
+  if (PASS == 0) {
+    for (int i = warp; i < n; i += nwarps) {
+      const float4 pc = sm.pos[i];
+      int cnt = 0;
+      for (int w = 0; w < words; w++) {
+        const int j = w * 32 + lane;
+        bool ok = false;
+        if (j < n) {
+          ok = pass_pred(pair_dr2<false>(pc, sm.pos[j], p), p);
+          if (j == i) ok = (p.flags & GAMD_NBR_SELF) != 0;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) mask[(size_t)i * words + w] = m;
+        cnt += __popc(m);
+      }
+      if (lane == 0) {
+        sm.deg[i] = cnt;
+        deg_g[base + i] = cnt;
+      }
+    }
+    if (!FUSED) return;
+    __syncthreads();
+    // block-wide exclusive scan of deg[0..n) (n <= 1024 = one element per thread)
+    const int v = tid < n ? sm.deg[tid] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) sm.warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int ws = lane < nwarps ? sm.warp_sums[lane] : 0;
+      int winc = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      sm.warp_sums[lane] = winc - ws;
+      if (lane == 31) sm.warp_sums[32] = winc;
+    }
+    __syncthreads();
+    const int ex = inc - v + sm.warp_sums[warp];
+    const int total = sm.warp_sums[32];
+    __syncthreads();
+    if (tid < n) {
+      sm.deg[tid] = ex;
+      row_ptr[tid] = ex;
+    }
+    if (tid == 0) {
+      sm.deg[n] = total;
+      row_ptr[n] = total;
+      if (total > cap) {          // publish an empty edge list (see k_nbr_guard)
+        atomicOr(err_flag, 1);
+        err_flag[1] = total;
+        *n_edges = 0;
+      } else {
+        *n_edges = total;
+      }
+    }
+    __syncthreads();
+    if (total > cap) return;
+  }
+  // fill from the masks
+  for (int i = warp; i < n; i += nwarps) {
+    int out = FUSED ? sm.deg[i] : row_ptr[base + i];
+    if (!FUSED && row_ptr[base + i + 1] > cap) continue;
+    for (int w = 0; w < words; w++) {
+      const uint32_t m = mask[(size_t)i * words + w];
+      if ((m >> lane) & 1u) {
+        const int dst = out + __popc(m & ((1u << lane) - 1u));
+        col[dst] = base + w * 32 + lane;
+        edst[dst] = base + i;
+      }
+      out += __popc(m);
+    }
+  }
+}
+
+// engine path for frames of at most SMALL_MAX atoms (dr2 < rc^2, self pairs kept, wrapped positions)
+int nbr_small_frames(gamd_ctx* ctx, const double* d_x, double scale, const double* box64, const NbrParams& p,
+                     const float* d_feat, cudaStream_t st) {
+  const int n = p.atoms_per_frame, words = (n + 31) >> 5;
+  const int cap = (int)ctx->cap_edges;
+  if (p.n_frames == 1) {
+    const size_t smem = sizeof(SmallSmem) + (size_t)n * words * 4;
+    if (!(ctx->attr_mask & GAMD_ATTR_NBR_SMALL)) {
+      GAMD_CUDA(cudaFuncSetAttribute(k_nbr_small<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(SmallSmem) + SMALL_MAX * (SMALL_MAX / 32) * 4)));
+      ctx->attr_mask |= GAMD_ATTR_NBR_SMALL;
+    }
+    k_nbr_small<0, true><<<1, SMALL_THREADS, smem, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, d_feat, ctx->pos_nbr,
+                                                         ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm, ctx->inv_perm, ctx->deg,
+                                                         ctx->row_ptr, nullptr, ctx->col_idx, ctx->edge_dst, cap,
+                                                         ctx->n_edges, ctx->err_flag);
+    GAMD_LAUNCH_CHECK();
+  } else {
+    if ((int64_t)p.n_atoms * words > ctx->vl_cap / 32 * 32) {
+      ctx->err = "mask scratch too small for the per-frame neighbor search";
+      return GAMD_ECAPACITY;
+    }
+    uint32_t* gm = reinterpret_cast<uint32_t*>(ctx->vl_cand);     // scratch: the skin path is off for small frames
+    const size_t smem = sizeof(SmallSmem);
+    k_nbr_small<0, false><<<p.n_frames, 256, smem, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, d_feat, ctx->pos_nbr,
+                                                         ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm, ctx->inv_perm, ctx->deg,
+                                                         ctx->row_ptr, gm, ctx->col_idx, ctx->edge_dst, cap, ctx->n_edges,
+                                                         ctx->err_flag);
+    GAMD_LAUNCH_CHECK();
+    int rc = scan_with_total(ctx, ctx->deg, ctx->row_ptr, p.n_atoms, ctx->n_edges, st);
+    if (rc) return rc;
+    k_nbr_guard<<<1, 1, 0, st>>>(ctx->row_ptr, p.n_atoms, cap, ctx->n_edges, ctx->err_flag);
+    GAMD_LAUNCH_CHECK();
+    k_nbr_small<1, false><<<p.n_frames, 256, smem, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, d_feat, ctx->pos_nbr,
+                                                         ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm, ctx->inv_perm, ctx->deg,
+                                                         ctx->row_ptr, gm, ctx->col_idx, ctx->edge_dst, cap, ctx->n_edges,
+                                                         ctx->err_flag);
+    GAMD_LAUNCH_CHECK();
+  }
+  ctx->last_nbr = p;
+  ctx->vl_key = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // Verlet-skin reuse (the reference: jax-md neighbor_list with dr_threshold = cutoff / 6 rebuilds its candidate
 // list only when an atom has moved more than half the skin, and re-applies the exact mask every step,
 // code/graph_utils.py:21-25, :36-44, :51-61).  Same here, without a host round trip:
