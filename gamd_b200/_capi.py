@@ -101,6 +101,11 @@ SIGNATURES = {
     "gamd_dd_pack_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "gamd_dd_unpack_rows": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "gamd_dd_finish": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p]),
+    "gamd_peer_alloc": (c_int32, [c_void_p, c_int64, POINTER(c_void_p), c_void_p]),
+    "gamd_peer_open": (c_int32, [c_void_p, c_void_p, POINTER(c_void_p)]),
+    "gamd_dd_push_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
+    "gamd_dd_push_bytes": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
+    "gamd_dd_wait_flag": (c_int32, [c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
     "gamd_check_async_errors": (c_int32, [c_void_p, c_void_p]),
     "gamd_debug_ptr": (c_int32, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
     "gamd_launch_count": (c_int64, [c_void_p]),
@@ -360,6 +365,42 @@ class Context:
         a, b = c_int64(), c_int64()
         self._check(self.lib.gamd_neighbor_stats(self._h, ctypes.byref(a), ctypes.byref(b), _stream()))
         return a.value, b.value
+
+    # ---- halo exchange over peer memory (CUDA IPC) ----
+    def peer_alloc(self, n_bytes):
+        """(device pointer, 64-byte IPC handle) of a zeroed buffer the neighbouring ranks may write."""
+        p = c_void_p()
+        h = (ctypes.c_uint8 * 64)()
+        self._check(self.lib.gamd_peer_alloc(self._h, int(n_bytes), ctypes.byref(p), h))
+        return p.value, bytes(h)
+
+    def peer_open(self, handle):
+        p = c_void_p()
+        h = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self.lib.gamd_peer_open(self._h, h, ctypes.byref(p)))
+        return p.value
+
+    def dd_push_rows(self, local_idx_i32, remote_rows_ptr, remote_flag_ptr, seq):
+        self._check(self.lib.gamd_dd_push_rows(self._h, _ptr(local_idx_i32), local_idx_i32.shape[0], remote_rows_ptr,
+                                               remote_flag_ptr, int(seq), _stream()))
+
+    def dd_push_bytes(self, src, remote_ptr, remote_flag_ptr, seq):
+        self._check(self.lib.gamd_dd_push_bytes(self._h, _ptr(src), src.numel() * src.element_size(), remote_ptr,
+                                                remote_flag_ptr, int(seq), _stream()))
+
+    def dd_wait_flag(self, flag_ptr, seq):
+        self._check(self.lib.gamd_dd_wait_flag(self._h, flag_ptr, int(seq), _stream()))
+
+    def view(self, ptr, dtype, shape):
+        """torch view (no copy) of device memory owned by the library (peer buffers)."""
+        import torch
+        count = int(np.prod(shape))
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        iface = {"shape": (count * itemsize,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+        class _W:
+            __cuda_array_interface__ = iface
+        return torch.as_tensor(_W(), device=torch.device("cuda", self.device)).view(dtype).view(*shape)
 
     def check_async_errors(self):
         self._check(self.lib.gamd_check_async_errors(self._h, _stream()))

@@ -1,5 +1,6 @@
 // C ABI of libgamd_b200 (see include/gamd_b200.h for the contract of every entry point).
 #include "common.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -216,6 +217,25 @@ __global__ void k_dd_unpack(int64_t first, const int* __restrict__ inv_perm, int
   reinterpret_cast<float4*>(srcA + (size_t)s * 128)[lane] = reinterpret_cast<const float4*>(in + (size_t)k * 256 + 128)[lane];
 }
 
+// ---- halo exchange over NVLink peer memory (CUDA IPC): the pack kernel writes straight into the neighbour's buffer ----
+__global__ void k_dd_push_bytes(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n16) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+// after the pushing kernel (stream order): make its peer writes visible system-wide, then publish the sequence number
+__global__ void k_dd_signal(unsigned long long* remote_flag, unsigned long long seq) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(seq) : "memory");
+}
+__global__ void k_dd_wait(const unsigned long long* flag, unsigned long long seq, int* err_flag) {
+  unsigned long long v = 0;
+  for (unsigned long long it = 0; it < (1ull << 31); it++) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= seq) return;
+    __nanosleep(64);
+  }
+  atomicOr(err_flag, 8);       // the neighbour never delivered (bounded wait instead of a hang)
+}
+
 int pack_pos_feat(gamd_ctx* ctx, const float* d_pos, const float* d_feat, int64_t n, float4* out, cudaStream_t st) {
   k_pack_pos_feat<<<ceil_div(n, 256), 256, 0, st>>>(d_pos, d_feat, n, out);
   GAMD_LAUNCH_CHECK();
@@ -294,6 +314,8 @@ int gamd_destroy(gamd_ctx* ctx) {
   if (ctx->d_wimg_node) cudaFree(ctx->d_wimg_node);
   if (ctx->d_bond) cudaFree(ctx->d_bond);
   if (ctx->d_nhc) cudaFree(ctx->d_nhc);
+  for (void* p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
+  for (void* p : ctx->peer_allocs) cudaFree(p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   if (ctx->graph_stream) cudaStreamDestroy(ctx->graph_stream);
@@ -651,6 +673,10 @@ int gamd_check_async_errors(gamd_ctx* ctx, void* stream) {
   if (flag[0] & 2) {
     ctx->err = "edge list must be sorted by centre with ids in [0, n_atoms)";
     return GAMD_EINVAL;
+  }
+  if (flag[0] & 8) {
+    ctx->err = "halo exchange: the neighbouring rank did not deliver its rows (peer-memory flag wait timed out)";
+    return GAMD_ESTATE;
   }
   if (flag[0] & 4) {
     ctx->vl_key = 0;
@@ -1200,6 +1226,76 @@ int gamd_dd_unpack_rows(gamd_ctx* ctx, int64_t first_local_idx, int64_t n, const
   GAMD_ENTER(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   k_dd_unpack<<<ceil_div(n * 32, 256), 256, 0, st>>>(first_local_idx, ctx->inv_perm, n, d_in, ctx->hn, ctx->srcA);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int gamd_peer_alloc(gamd_ctx* ctx, int64_t n_bytes, void** d_ptr, uint8_t h_handle[64]) {
+  if (!ctx || n_bytes <= 0 || !d_ptr || !h_handle) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  GAMD_CUDA(cudaMalloc(&p, (size_t)n_bytes));
+  GAMD_CUDA(cudaMemset(p, 0, (size_t)n_bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    ctx->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+    return GAMD_ECUDA;
+  }
+  memcpy(h_handle, &h, 64);
+  ctx->peer_allocs.push_back(p);
+  *d_ptr = p;
+  return 0;
+}
+
+int gamd_peer_open(gamd_ctx* ctx, const uint8_t h_handle[64], void** d_ptr) {
+  if (!ctx || !h_handle || !d_ptr) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, h_handle, 64);
+  void* p = nullptr;
+  GAMD_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->peer_opened.push_back(p);
+  *d_ptr = p;
+  return 0;
+}
+
+int gamd_dd_push_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, float* d_remote_rows,
+                      unsigned long long* d_remote_flag, uint64_t seq, void* stream) {
+  if (!ctx || ctx->dd_n_loc <= 0 || n < 0 || !d_remote_flag || (n > 0 && (!d_local_idx || !d_remote_rows))) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0) {
+    k_dd_pack<<<ceil_div(n * 32, 256), 256, 0, st>>>(d_local_idx, ctx->inv_perm, n, ctx->hn, ctx->srcA, d_remote_rows);
+    GAMD_LAUNCH_CHECK();
+  }
+  k_dd_signal<<<1, 1, 0, st>>>(d_remote_flag, (unsigned long long)seq);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int gamd_dd_push_bytes(gamd_ctx* ctx, const void* d_src, int64_t n_bytes, void* d_remote_dst,
+                       unsigned long long* d_remote_flag, uint64_t seq, void* stream) {
+  if (!ctx || n_bytes < 0 || (n_bytes & 15) || !d_remote_flag || (n_bytes > 0 && (!d_src || !d_remote_dst))) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_bytes > 0) {
+    const int64_t n16 = n_bytes / 16;
+    const int blocks = (int)std::min<int64_t>(ceil_div(n16, 256), 4 * ctx->sm_count);
+    k_dd_push_bytes<<<blocks, 256, 0, st>>>(static_cast<const float4*>(d_src), static_cast<float4*>(d_remote_dst), n16);
+    GAMD_LAUNCH_CHECK();
+  }
+  k_dd_signal<<<1, 1, 0, st>>>(d_remote_flag, (unsigned long long)seq);
+  GAMD_LAUNCH_CHECK();
+  return 0;
+}
+
+int gamd_dd_wait_flag(gamd_ctx* ctx, const unsigned long long* d_flag, uint64_t seq, void* stream) {
+  if (!ctx || !d_flag || !ctx->arena) return GAMD_EINVAL;
+  GAMD_ENTER(ctx);
+  k_dd_wait<<<1, 1, 0, (cudaStream_t)stream>>>(d_flag, (unsigned long long)seq, ctx->err_flag);
   GAMD_LAUNCH_CHECK();
   return 0;
 }

@@ -125,6 +125,8 @@ struct gamd_ctx {
   int dd_reserve_sms = 0;
   int mp_variant = 0;
 
+  // halo exchange over peer memory: buffers this rank exposes (cudaMalloc + IPC handle) / neighbours' buffers it opened
+  std::vector<void*> peer_allocs, peer_opened;
   // thermostat / constraints of the device-resident loop (gamd_md_configure)
   gamd_md_options md{};
   uint64_t md_generation = 0;

@@ -127,6 +127,63 @@ def _nonzero_n(mask, n):
     return torch.nonzero(mask).flatten()
 
 
+class PeerHalo:
+    """Fixed-capacity halo exchange WITHOUT a collective: every rank exposes one device buffer (CUDA IPC), its two
+    neighbours map it, and the pack kernel writes the rows straight into the neighbour's buffer over NVLink / NVSwitch
+    peer memory; a system-scope release store of a sequence number follows in stream order and the receiver's stream
+    waits for it (``gamd_dd_push_rows`` / ``gamd_dd_push_bytes`` / ``gamd_dd_wait_flag``).  Measured on 2 B200: an
+    ncclSend/Recv pair for the 26 MB feature rows of a face takes 0.44 ms (NCCL's p2p channels), the peer write
+    runs at NVLink rate.
+
+    Buffers are double-buffered by the parity of the sequence number: rank A's push k+2 reuses the slot of push k only
+    after A has waited for B's push k+1, which B's stream issued after it consumed push k."""
+    ROW_W = 256        # floats per row: [LN(h) | src_affine(LN(h))]
+
+    def __init__(self, ctx, plan, cap, pos_w):
+        self.ctx, self.plan, self.cap, self.pos_w = ctx, plan, int(cap), int(pos_w)
+        assert self.cap % 2 == 0
+        self.row_bytes = self.cap * self.ROW_W * 4
+        self.pos_bytes = self.cap * self.pos_w * 8
+        total = 256 + 4 * self.row_bytes + 4 * self.pos_bytes
+        self.base, handle = ctx.peer_alloc(total)
+        handles = [None] * plan.world
+        dist.all_gather_object(handles, handle)
+        self.left = ctx.peer_open(handles[plan.left])
+        self.right = self.left if plan.right == plan.left else ctx.peer_open(handles[plan.right])
+        self.seq_pos = self.seq_rows = 0
+
+    # flags: 0 positions from left, 1 positions from right, 2 rows from left, 3 rows from right
+    def _rows(self, base, par, side):
+        return base + 256 + (par * 2 + side) * self.row_bytes
+
+    def _pos(self, base, par, side):
+        return base + 256 + 4 * self.row_bytes + (par * 2 + side) * self.pos_bytes
+
+    def exchange_pos(self, send_l, send_r):
+        """[cap, pos_w] fp64 rows for the left / right neighbour -> (from_left, from_right) views of my buffer."""
+        self.seq_pos += 1
+        seq, par, c = self.seq_pos, self.seq_pos & 1, self.ctx
+        c.dd_push_bytes(send_l.contiguous(), self._pos(self.left, par, 1), self.left + 8 * 1, seq)
+        c.dd_push_bytes(send_r.contiguous(), self._pos(self.right, par, 0), self.right + 8 * 0, seq)
+        c.dd_wait_flag(self.base + 8 * 0, seq)
+        c.dd_wait_flag(self.base + 8 * 1, seq)
+        shape = (self.cap, self.pos_w)
+        return (c.view(self._pos(self.base, par, 0), torch.float64, shape),
+                c.view(self._pos(self.base, par, 1), torch.float64, shape))
+
+    def exchange_rows(self, idx_l, idx_r):
+        """feature rows of my atoms idx_l / idx_r (int32, cap entries each) -> (from_left, from_right) row buffers."""
+        self.seq_rows += 1
+        seq, par, c = self.seq_rows, self.seq_rows & 1, self.ctx
+        c.dd_push_rows(idx_l, self._rows(self.left, par, 1), self.left + 8 * 3, seq)
+        c.dd_push_rows(idx_r, self._rows(self.right, par, 0), self.right + 8 * 2, seq)
+        c.dd_wait_flag(self.base + 8 * 2, seq)
+        c.dd_wait_flag(self.base + 8 * 3, seq)
+        shape = (self.cap, self.ROW_W)
+        return (c.view(self._rows(self.base, par, 0), torch.float32, shape),
+                c.view(self._rows(self.base, par, 1), torch.float32, shape))
+
+
 class CudaBackend:
     """Force evaluation on owned + halo atoms through the C ABI (``gamd_dd_*``)."""
 
@@ -193,8 +250,13 @@ class SlabDomainMD:
         self.n_halo = (0, 0)
         self.migrate_every = int(migrate_every)
         self._since_migration = 0
-        self.halo_cap = None if halo_cap is None or plan.world == 1 else int(halo_cap)
+        self.halo_cap = None if halo_cap is None or plan.world == 1 else int(halo_cap) // 2 * 2
         self._halo_max = torch.zeros(2, dtype=torch.int64, device=x_nm.device)
+        # one GPU per rank (NCCL backend): the halo travels by direct peer-memory writes instead of ncclSend/Recv
+        self.peer = None
+        if (self.halo_cap is not None and x_nm.is_cuda and dist.is_initialized() and dist.get_backend() == "nccl"
+                and hasattr(backend, "ctx") and os.environ.get("GAMD_DD_PEER", "1") != "0"):
+            self.peer = PeerHalo(backend.ctx, plan, self.halo_cap, 3 if feat is None else 4)
 
     # ---- construction ------------------------------------------------------------------------------
     @staticmethod
@@ -316,7 +378,10 @@ class SlabDomainMD:
         def take(idx):
             return torch.where((idx >= 0)[:, None], rows[idx.clamp(min=0)], pad)
 
-        h_l, h_r = _exchange(take(idx_l), take(idx_r), p, cap, cap)
+        if self.peer is not None:
+            h_l, h_r = self.peer.exchange_pos(take(idx_l), take(idx_r))
+        else:
+            h_l, h_r = _exchange(take(idx_l), take(idx_r), p, cap, cap)
         self.n_halo = (cap, cap)
         local = torch.cat([rows, h_l, h_r])
         pos_local = local[:, 0:3].contiguous()
@@ -327,7 +392,10 @@ class SlabDomainMD:
         for l in range(be.n_layers):
             be.layer(l)
             if l + 1 < be.n_layers:
-                r_l, r_r = _exchange(be.pack(i_l), be.pack(i_r), p, cap, cap)
+                if self.peer is not None:
+                    r_l, r_r = self.peer.exchange_rows(i_l, i_r)       # pack kernel writes into the neighbours' memory
+                else:
+                    r_l, r_r = _exchange(be.pack(i_l), be.pack(i_r), p, cap, cap)
                 be.unpack(n_own, r_l)
                 be.unpack(n_own + cap, r_r)
         if dt_kick is None:

@@ -281,6 +281,23 @@ int gamd_dd_pack_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, floa
 int gamd_dd_unpack_rows(gamd_ctx* ctx, int64_t first_local_idx, int64_t n, const float* d_in, void* stream);
 int gamd_dd_finish(gamd_ctx* ctx, double* d_force, double* d_v, const double* d_mass, double dt, double* d_ke,
                    void* stream);
+/* Halo exchange over NVLink / NVSwitch PEER MEMORY instead of NCCL send/recv (one process per GPU; the buffers are
+ * shared with CUDA IPC):
+ *   gamd_peer_alloc  device buffer of this rank that neighbours may write (zeroed) + its 64-byte IPC handle
+ *   gamd_peer_open   map a neighbour's buffer from its handle (exchanged by the caller, e.g. all_gather)
+ *   gamd_dd_push_rows  the rows [hn | src_affine(hn)] of the listed owned atoms are written by the pack kernel
+ *                    STRAIGHT INTO the neighbour's buffer (no staging copy, no collective); a system-scope release
+ *                    store of `seq` to the neighbour's flag follows in stream order
+ *   gamd_dd_push_bytes the same for a plain device buffer (halo positions); n_bytes must be a multiple of 16
+ *   gamd_dd_wait_flag  stream-ordered wait until this rank's own flag has reached `seq` (bounded: a neighbour that never
+ *                    delivers raises GAMD_ESTATE at the next gamd_check_async_errors instead of hanging the GPU) */
+int gamd_peer_alloc(gamd_ctx* ctx, int64_t n_bytes, void** d_ptr, uint8_t h_handle[64]);
+int gamd_peer_open(gamd_ctx* ctx, const uint8_t h_handle[64], void** d_ptr);
+int gamd_dd_push_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, float* d_remote_rows,
+                      unsigned long long* d_remote_flag, uint64_t seq, void* stream);
+int gamd_dd_push_bytes(gamd_ctx* ctx, const void* d_src, int64_t n_bytes, void* d_remote_dst,
+                       unsigned long long* d_remote_flag, uint64_t seq, void* stream);
+int gamd_dd_wait_flag(gamd_ctx* ctx, const unsigned long long* d_flag, uint64_t seq, void* stream);
 
 /* synchronises `stream` and reports errors raised asynchronously on the device since the
  * last check (GAMD_ECAPACITY: edge capacity exceeded; GAMD_EINVAL: edge list not sorted by

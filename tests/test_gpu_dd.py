@@ -125,15 +125,18 @@ def test_slab_md_split_layers_equals_single_domain():
     assert abs(ret["ke"] - ke_ref) / ke_ref <= 1e-6
 
 
-def test_slab_md_fixed_capacity_halo_equals_single_domain():
-    """world 3, lazy hand-over, FIXED-size halo messages (1500 slots per face, unused ones NaN-padded): the steps
-    between hand-overs run without any host synchronisation and give the same trajectory as one domain."""
+@pytest.mark.parametrize("world,cap", [(2, 2200), (3, 1500)])
+def test_slab_md_fixed_capacity_halo_equals_single_domain(world, cap):
+    """lazy hand-over, FIXED-size halo messages (unused slots NaN-padded): the steps between hand-overs run without
+    any host synchronisation and give the same trajectory as one domain.  With one GPU per rank (gpurun --gpus N) the
+    halo travels by direct peer-memory writes (dist.PeerHalo: gamd_dd_push_rows / _push_bytes / _wait_flag over CUDA
+    IPC), otherwise (ranks sharing a GPU) through gloo."""
     from gamd_b200 import _capi
     f_ref, x_ref, ke_ref = _reference(_capi.PREC_BF16X3)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(3, _free_port(), _capi.PREC_BF16X3, ret, 3, 0.3, False, 1500), nprocs=3, join=True)
-    assert ret["halo"] == (1500, 1500)
+    mp.spawn(_worker, args=(world, _free_port(), _capi.PREC_BF16X3, ret, 3, 0.3, False, cap), nprocs=world, join=True)
+    assert ret["halo"] == (cap, cap)
     assert np.abs(ret["f0"] - f_ref).max() / np.abs(f_ref).max() <= 1e-4
     assert np.abs(ret["x5"] - x_ref).max() <= 1e-7
     assert abs(ret["ke"] - ke_ref) / ke_ref <= 1e-6
