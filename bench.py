@@ -47,7 +47,7 @@ WORKLOADS = {
 }
 FIX = os.path.join(ROOT, "tests", "golden", "fixtures")
 DT = 0.002  # ps (test_nosehoover.py:29)
-DD_MIGRATE_EVERY, DD_MARGIN = 4, 0.5   # domain decomposition: atom hand-over interval (steps), halo margin (A)
+DD_MIGRATE_EVERY, DD_MARGIN = 8, 0.8   # domain decomposition: atom hand-over interval (steps), halo margin (A)
 
 
 def build_system(name, seed=42):
@@ -250,11 +250,12 @@ def run_ours(args):
         ctx.load_state_dict(random_state_dict(0, kind=kind))
         ctx.set_scaler(s_np["mean"], s_np["var"])
         ctx.finalize()
-        # atoms are handed to the neighbouring slab every 4th step; the halo is 0.5 A wider so that an owner can keep
-        # integrating a stray atom exactly in between (thermal drift over 4 steps is < 0.1 A; checked at every migration)
+        # atoms are handed to the neighbouring slab every 8th step; the halo is 0.8 A wider so that an owner can keep
+        # integrating a stray atom, and a rank can keep its halo lists, exactly in between (thermal drift over 8 steps
+        # is ~0.1 A; the largest displacement is checked against half the margin at every hand-over)
         plan = SlabPlan(box, rc, world, rank, margin=DD_MARGIN if world > 1 else 0.0)
         # fixed-size halo messages (unused slots padded): no per-step host synchronisation between migrations
-        halo_cap = (int(1.3 * (n_total / world) * plan.halo / plan.width) + 2048) if world > 1 else None
+        halo_cap = (int(1.15 * (n_total / world) * plan.halo / plan.width) + 1024) if world > 1 else None
         n_loc_cap = int((n_total / world) * 1.15) + 2 * (halo_cap or 0) + 4096
         ctx.reserve(n_loc_cap, int(n_total / world * 1.1 + 4096) * 34)
         md = SlabDomainMD.scatter_global(CudaBackend(ctx, box, rc, 4, overlap=os.environ.get("GAMD_DD_OVERLAP", "0") == "1"),
@@ -281,8 +282,9 @@ def run_ours(args):
                 d = float((f_all - f_one).abs().max())
                 fmax = float(f_one.abs().max())
                 frms = float((f_one - f_one.mean(0)).pow(2).mean().sqrt())
-                dd_check = {"what": "forces of the initial configuration: slab decomposition over %d ranks (NCCL halo "
-                                    "exchange per layer) vs ONE single-domain evaluation of the whole box on rank 0" % world,
+                dd_check = {"what": "forces of the initial configuration: slab decomposition over %d ranks (halo exchange "
+                                    "per layer over %s) vs ONE single-domain evaluation of the whole box on rank 0"
+                                    % (world, "NVLink peer memory" if md.peer is not None else "NCCL send/recv"),
                             "atoms": n_total, "err_over_max_F": d / fmax, "err_over_rms_F": d / frms, "tol_over_max_F": 1e-4,
                             "ok": bool(d / fmax <= 1e-4)}
                 ctx1.close()
@@ -485,7 +487,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "atoms_per_gpu": n,
                    "edges_per_gpu": n_edges, "model": "MDNet 128/128/128 x4 layers, random-init (numpy PCG64 seed 0)",
-                   "parallelism": ("slab domain decomposition x%d, NCCL halo exchange per MP layer, atom hand-over "
+                   "parallelism": ("slab domain decomposition x%d, halo exchange per MP layer by peer-memory writes over NVLink, atom hand-over "
                                    "every %d steps (halo margin %.1f A), fixed-capacity halo messages (no host sync "
                                    "between hand-overs)" % (world, DD_MIGRATE_EVERY, DD_MARGIN)
                                    if mode == "dd" and world > 1 else "slab domain decomposition x1" if mode == "dd"

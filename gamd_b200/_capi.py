@@ -110,6 +110,7 @@ SIGNATURES = {
     "gamd_debug_ptr": (c_int32, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
     "gamd_launch_count": (c_int64, [c_void_p]),
     "gamd_neighbor_stats": (c_int32, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p]),
+    "gamd_neighbor_invalidate": (c_int32, [c_void_p]),
     "gamd_profile_enable": (c_int32, [c_void_p, c_int32]),
     "gamd_profile_read": (c_int32, [c_void_p, c_char_p, POINTER(c_double), POINTER(c_int64)]),
 }
@@ -359,6 +360,9 @@ class Context:
 
     def dd_finish(self, force, v=None, mass=None, dt=0.0, ke=None):
         self._check(self.lib.gamd_dd_finish(self._h, _ptr(force), _ptr(v), _ptr(mass), float(dt), _ptr(ke), _stream()))
+
+    def neighbor_invalidate(self):
+        self._check(self.lib.gamd_neighbor_invalidate(self._h))
 
     def neighbor_stats(self):
         """(candidate rebuilds, searches) of the skin-reusing neighbor path since the last reserve."""

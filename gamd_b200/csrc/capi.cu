@@ -1143,8 +1143,14 @@ int gamd_dd_begin(gamd_ctx* ctx, const double* d_pos, int64_t n_own, int64_t n_l
   if ((rc = nbr_setup_params(ctx, n_local, 1, boxf, cutoff, GAMD_NBR_LT | GAMD_NBR_SELF, &p))) return rc;
   p.n_centers = (int)n_own;
   prof_mark(ctx, "neighbor", st);
-  if ((rc = nbr_bin_f64(ctx, d_pos, 1.0, h_box, p, st))) return rc;
-  if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
+  if (ctx->vl_skin_frac > 0.f && n_local >= ctx->vl_min_atoms && ctx->vl_cap < (int64_t(1) << 31)) {
+    // candidate reuse while the caller keeps the local atom set unchanged (gamd_neighbor_invalidate after a change)
+    if ((rc = nbr_step_verlet(ctx, d_pos, 1.0, h_box, p, d_feat, st))) return rc;
+  } else {
+    if ((rc = nbr_bin_f64(ctx, d_pos, 1.0, h_box, p, st))) return rc;
+    if ((rc = nbr_sort_and_sweep(ctx, p, d_feat, st))) return rc;
+    ctx->vl_key = 0;
+  }
   prof_mark(ctx, "neighbor", st);
   ctx->dd_n_own = n_own;
   ctx->dd_n_loc = n_local;
@@ -1337,6 +1343,12 @@ int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_byt
 }
 
 int64_t gamd_launch_count(const gamd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gamd_neighbor_invalidate(gamd_ctx* ctx) {
+  if (!ctx) return GAMD_EINVAL;
+  ctx->vl_epoch++;
+  return 0;
+}
 
 int gamd_neighbor_stats(gamd_ctx* ctx, int64_t* n_rebuilds, int64_t* n_searches, void* stream) {
   if (!ctx || !ctx->arena) return GAMD_EINVAL;

@@ -196,10 +196,14 @@ class CudaBackend:
         from . import _capi
         self.split_layers = bool(overlap) and ctx.precision != _capi.PREC_FP32
 
-    def begin(self, pos_local, n_own, feat_local):
+    def begin(self, pos_local, n_own, feat_local, stable=False):
+        """``stable``: the local atoms are the SAME atoms in the same order as in the previous call (frozen halo
+        lists between two hand-overs) - the neighbor candidates may be reused."""
         n_loc = pos_local.shape[0]
         if n_loc > self.ctx.cap_atoms:
             self.ctx.reserve(int(n_loc * 1.2), int(self.ctx.cap_edges * 1.2 * n_loc / max(self.ctx.cap_atoms, 1)))
+        if not stable:
+            self.ctx.neighbor_invalidate()
         self.ctx.dd_begin(pos_local, n_own, self.box, self.cutoff, feat=feat_local)
 
     def layer(self, l):
@@ -241,7 +245,10 @@ class SlabDomainMD:
         ``halo_cap`` (atoms per face, the same on every rank) makes the steps BETWEEN migrations free of host
         synchronisation: halo messages have a fixed size, unused slots carry NaN positions (a NaN never passes the
         neighbor predicate, so a padded slot has no edges and its feature rows are never read), the true counts stay on
-        the device and are checked against the capacity at the next migration."""
+        the device and are checked against the capacity at the next migration.  The halo MEMBERSHIP is chosen at a
+        hand-over and frozen until the next one (the same atoms are re-sent every step), so the local atom set is
+        stable and the neighbor search reuses its candidate rows; this is exact while no atom has moved more than half
+        the margin since the hand-over (checked there)."""
         if int(migrate_every) > 1 and plan.margin <= 0.0:
             raise ValueError("migrate_every > 1 needs a SlabPlan with margin > 0")
         self.be, self.plan = backend, plan
@@ -252,6 +259,9 @@ class SlabDomainMD:
         self._since_migration = 0
         self.halo_cap = None if halo_cap is None or plan.world == 1 else int(halo_cap) // 2 * 2
         self._halo_max = torch.zeros(2, dtype=torch.int64, device=x_nm.device)
+        self._idx = None               # frozen halo lists (idx_l, idx_r, int32 clamped copies) of the current interval
+        self._x_mig = None             # positions at the last halo selection
+        self._topo_changed = True
         # one GPU per rank (NCCL backend): the halo travels by direct peer-memory writes instead of ncclSend/Recv
         self.peer = None
         if (self.halo_cap is not None and x_nm.is_cuda and dist.is_initialized() and dist.get_backend() == "nccl"
@@ -286,8 +296,17 @@ class SlabDomainMD:
         stray = dx.abs() - half
         far = stray >= p.width                                    # beyond the adjacent slab
         over = stray > p.margin + 1e-9 if self.migrate_every > 1 else torch.zeros_like(far)
-        mine = torch.stack([go_l.sum(), go_r.sum(), far.sum(), over.sum(), self._halo_max.max()])
+        moved = torch.zeros((), dtype=torch.int64, device=dx.device)
+        if self.halo_cap is not None and self._x_mig is not None and self._x_mig.shape == self.x.shape:
+            # largest displacement since the halo lists were frozen, in 1e-6 Angstrom
+            moved = ((self.x - self._x_mig).norm(dim=1).max() * 1e7).long()
+        mine = torch.stack([go_l.sum(), go_r.sum(), far.sum(), over.sum(), self._halo_max.max(), moved])
         table = _gather_stats(mine, p)
+        if self.halo_cap is not None:
+            self._idx = None           # new halo lists at the next force evaluation
+            if int(table[:, 5].max()) * 1e-6 > 0.5 * p.margin + 1e-9:
+                raise RuntimeError(f"an atom moved {int(table[:, 5].max()) * 1e-6:.3f} A since the halo lists were frozen, "
+                                   f"more than half the margin ({p.margin} A): hand over more often or widen the margin")
         if self.halo_cap is not None and int(table[:, 4].max()) > self.halo_cap:
             raise RuntimeError(f"halo capacity exceeded: {int(table[:, 4].max())} atoms within the cutoff of a slab face, "
                                f"capacity {self.halo_cap}; forces since the previous migration are incomplete")
@@ -363,12 +382,17 @@ class SlabDomainMD:
     def _compute_forces_fixed_cap(self, pos, dt_kick):
         """the same step with fixed-size halo messages: no host synchronisation anywhere."""
         p, be, cap = self.plan, self.be, self.halo_cap
-        to_l, to_r = p.halo_masks_centered(p.centered(pos[:, 0]))
-        if p.world == 2:
-            to_r = to_r & ~to_l
-        self._halo_max = torch.maximum(self._halo_max, torch.stack([to_l.sum(), to_r.sum()]))
-        idx_l = torch.nonzero_static(to_l, size=cap, fill_value=-1).flatten()
-        idx_r = torch.nonzero_static(to_r, size=cap, fill_value=-1).flatten()
+        if self._idx is None:
+            to_l, to_r = p.halo_masks_centered(p.centered(pos[:, 0]))
+            if p.world == 2:
+                to_r = to_r & ~to_l
+            self._halo_max = torch.maximum(self._halo_max, torch.stack([to_l.sum(), to_r.sum()]))
+            idx_l = torch.nonzero_static(to_l, size=cap, fill_value=-1).flatten()
+            idx_r = torch.nonzero_static(to_r, size=cap, fill_value=-1).flatten()
+            self._idx = (idx_l, idx_r, idx_l.clamp(min=0).to(torch.int32), idx_r.clamp(min=0).to(torch.int32))
+            self._x_mig = self.x.clone()
+            self._topo_changed = True
+        idx_l, idx_r, i_l, i_r = self._idx
         cols = [pos] if self.feat is None else [pos, self.feat[:, None].to(torch.float64)]
         rows = torch.cat(cols, dim=1)
         pad = torch.full((1, rows.shape[1]), float("nan"), dtype=rows.dtype, device=rows.device)
@@ -387,8 +411,8 @@ class SlabDomainMD:
         pos_local = local[:, 0:3].contiguous()
         feat_local = None if self.feat is None else local[:, 3].float().contiguous()
         n_own = pos.shape[0]
-        be.begin(pos_local, n_own, feat_local)
-        i_l, i_r = idx_l.clamp(min=0).to(torch.int32), idx_r.clamp(min=0).to(torch.int32)
+        be.begin(pos_local, n_own, feat_local, stable=not self._topo_changed)
+        self._topo_changed = False
         for l in range(be.n_layers):
             be.layer(l)
             if l + 1 < be.n_layers:

@@ -312,6 +312,10 @@ int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_byt
  * only when an atom has moved more than half the skin, dr_threshold = cutoff / 6, and applies the exact mask every
  * step): number of candidate rebuilds and of searches since gamd_reserve.  Synchronises `stream`. */
 int gamd_neighbor_stats(gamd_ctx* ctx, int64_t* n_rebuilds, int64_t* n_searches, void* stream);
+/* the atoms behind the indices changed (hand-over between domains, new halo membership): the saved candidate rows
+ * describe other atoms and must be rebuilt by the next search.  gamd_dd_begin reuses candidates only between two
+ * calls of this function; the single-domain entry points detect a new system by its size / box / cutoff. */
+int gamd_neighbor_invalidate(gamd_ctx* ctx);
 /* number of kernel launches issued by this ctx since creation */
 int64_t gamd_launch_count(const gamd_ctx* ctx);
 /* per-stage CUDA-event timers on the launching stream.  Stages: "neighbor", "edge_encode",

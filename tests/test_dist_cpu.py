@@ -37,7 +37,7 @@ class FakeBackend:
         self.log = []
         self.box = box
 
-    def begin(self, pos_local, n_own, feat_local):
+    def begin(self, pos_local, n_own, feat_local, stable=False):
         self.pos, self.n_own, self.gid = pos_local.numpy(), n_own, feat_local.numpy().round().astype(np.int64)
         real = self.gid >= 0                                       # fixed-capacity halo: unused slots carry gid -1, NaN
         assert np.isnan(self.pos[~real]).all()
@@ -197,7 +197,7 @@ def _worker_fixed_cap(rank, world, port, ret):
         x = rng.uniform(0, BOX, (n, 3)) / 10.0
         v = rng.standard_normal((n, 3)) * 0.3
         m = np.full(n, 39.9)
-        plan = SlabPlan(BOX, RC, world, rank, margin=1.5)
+        plan = SlabPlan(BOX, RC, world, rank, margin=3.0)       # atoms move up to ~1 A between hand-overs here
         md = SlabDomainMD.scatter_global(FakeBackend(), plan, x, v, m, "cpu", feat_all=np.arange(n, dtype=np.float32),
                                          migrate_every=3, halo_cap=260)
         md.compute_forces()
