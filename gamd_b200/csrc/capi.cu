@@ -294,6 +294,8 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   ctx->vl_skin_frac = getenv("GAMD_NBR_SKIN") ? (float)atof(getenv("GAMD_NBR_SKIN")) : (1.f / 6.f);
   if (getenv("GAMD_NBR_SKIN_MIN_ATOMS")) ctx->vl_min_atoms = atoll(getenv("GAMD_NBR_SKIN_MIN_ATOMS"));
   ctx->small_frames = !(getenv("GAMD_NBR_SMALL") && atoi(getenv("GAMD_NBR_SMALL")) == 0);
+  if (getenv("GAMD_MP_SMALL_ATOMS")) ctx->mp_small_atoms = atoi(getenv("GAMD_MP_SMALL_ATOMS"));
+  if (getenv("GAMD_ENC_VARIANT")) ctx->enc_variant = atoi(getenv("GAMD_ENC_VARIANT"));
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (ctx->sm_count < 2 && ctx->mp_variant >= 5) ctx->mp_variant = 0;

@@ -124,6 +124,9 @@ struct gamd_ctx {
   bool dbg_timeline = false;
   int dd_reserve_sms = 0;
   int mp_variant = 0;
+  int enc_variant = 3;         // edge encoder: 3 = three tiles in flight (in-place TMEM operands), 0 = two tiles
+  int64_t model_atoms = 0;     // atoms of the forward pass in flight (model_begin)
+  int mp_small_atoms = 4096;   // systems up to this size use the two-tile single-CTA edge kernel (GAMD_MP_SMALL_ATOMS)
 
   // halo exchange over peer memory: buffers this rank exposes (cudaMalloc + IPC handle) / neighbours' buffers it opened
   std::vector<void*> peer_allocs, peer_opened;
@@ -168,7 +171,7 @@ void prof_mark(gamd_ctx* ctx, const char* stage, cudaStream_t st);   // call bef
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16, GAMD_ATTR_MP_TC2 = 32, GAMD_ATTR_NBR_SMALL = 64 };
+enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16, GAMD_ATTR_MP_TC2 = 32, GAMD_ATTR_NBR_SMALL = 64, GAMD_ATTR_ENC_TC3 = 128 };
 
 // every stream entry point runs on the context's device, whatever device the calling thread had current
 #define GAMD_ENTER(ctx)                                                                  \

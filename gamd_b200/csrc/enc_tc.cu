@@ -394,6 +394,353 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_encode_tc(EncTcArgs a) {
   if (warp == MMA_WARP) tmem_dealloc(tb, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Three tiles in flight (default): same arithmetic, the TMEM scheme of mp_tc3.cu / mp_tc2cta.cu - four blocks of 128
+// columns = three tile homes + one floating block, activations written IN PLACE over the accumulator (K step j of the
+// next operand at columns 16 j: 8 columns of bf16 hi pairs, 8 of lo pairs), a GEMM reads the home and writes the
+// floating block, which becomes the new home (published in shared memory before the commit).  The encoder needs no
+// gather staging and its 160 KB of weights are resident, so nothing couples the three tile chains.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NSLOT3 = 3;
+constexpr int EPI_WARPS3 = 8 * NSLOT3;
+constexpr int MMA_WARP3 = EPI_WARPS3;
+constexpr int THREADS3 = (EPI_WARPS3 + 2) * 32;
+
+struct __align__(1024) SmemEnc3 {
+  uint8_t w[W_TOTAL];          // enc0 hi, enc0 lo, enc2 hi, enc2 lo, enc4 hi, enc4 lo
+  float bias[3][128];
+  float ln_w[128], ln_b[128];
+  float centers[GAMD_NRBF];
+  float xch[NSLOT3][128][2];   // LayerNorm partial sums exchanged between the two column-half warps of a row
+  uint64_t w_full, a_ready[NSLOT3], d_ready[NSLOT3];
+  volatile uint32_t home[NSLOT3];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(THREADS3, 1) k_edge_encode_tc3(EncTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  SmemEnc3& sm = *reinterpret_cast<SmemEnc3*>(raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0 && (smem_u32(raw) & 1023u)) __trap();
+  const int E = *a.n_edges;
+  const int ntiles = (E + TILE - 1) / TILE;
+  const int ngroups = (ntiles + NSLOT3 - 1) / NSLOT3;
+  const bool exact = a.exact != 0;
+
+  if (warp == MMA_WARP3) tmem_alloc(&sm.tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&sm.w_full, 1);
+    for (int g = 0; g < NSLOT3; g++) {
+      mbar_init(&sm.a_ready[g], 256);
+      mbar_init(&sm.d_ready[g], 1);
+      sm.home[g] = g;
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 3 * 128; i += THREADS3) (&sm.bias[0][0])[i] = a.bias[i];
+  for (int i = tid; i < 128; i += THREADS3) {
+    sm.ln_w[i] = a.ln_w[i];
+    sm.ln_b[i] = a.ln_b[i];
+  }
+  if (tid < GAMD_NRBF) sm.centers[tid] = a.expand_edge ? a.centers[tid] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = sm.tmem_base;
+
+  if (warp < EPI_WARPS3) {
+    // ===== epilogue warps: thread = edge row; warp = (tile slot g, column half ch, lane quadrant wq) =====
+    const int g = warp >> 3, ch = (warp >> 2) & 1, wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const int col0 = ch * 64;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    uint32_t Hb = tb + lane_base + g * 128;          // my lanes of the slot's current home block
+    const uint32_t bias_addr = smem_u32(&sm.bias[0][col0]);
+    const int bar_id = 1 + g * 4 + wq;
+    uint32_t d_par = 0;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+      const int tile = grp * NSLOT3 + g;
+      if (tile >= ntiles) continue;
+      const int e = tile * TILE + r;
+      const bool valid = e < E;
+
+      // ---- stage 0 operand: edge features, my 32 of the 64 (zero padded) columns = K steps 2 ch, 2 ch + 1 ----
+      {
+        float ux = 0.f, uy = 0.f, uz = 0.f, dh = 0.f, flag = 0.f;
+        if (valid) {
+          const int c = a.edst[e], n = a.col[e];
+          const float4 pc = a.pos[c], pn = a.pos[n];
+          // rel = pos[neigh] - pos[center]; remainder(rel + L/2, L) - L/2   (nn_module.py:615-621)
+          float rr[3] = {pn.x - pc.x, pn.y - pc.y, pn.z - pc.z};
+          if (a.dynbox) { rr[0] = pc.x - pn.x; rr[1] = pc.y - pn.y; rr[2] = pc.z - pn.z; }
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            const float half = 0.5f * a.box[d];
+            const float t = __fadd_rn(rr[d], half);
+            float m = fmodf(t, a.box[d]);
+            if (m < 0.f) m = __fadd_rn(m, a.box[d]);
+            rr[d] = __fsub_rn(m, half);
+            if (a.dynbox) rr[d] = -rr[d];
+          }
+          const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rr[0], rr[0]), __fmul_rn(rr[1], rr[1])), __fmul_rn(rr[2], rr[2])));
+          const float den = dist + 1e-8f;
+          ux = rr[0] / den; uy = rr[1] / den; uz = rr[2] / den;
+          dh = (dist - a.length_mean) / a.length_std;
+          if (a.use_bond) {
+            const int ic = a.orig_id ? a.orig_id[c] : c, in = a.orig_id ? a.orig_id[n] : n;
+            if (ic / a.atoms_per_frame == in / a.atoms_per_frame) {
+              const int lc = ic % a.atoms_per_frame, ln = in % a.atoms_per_frame;
+#pragma unroll
+              for (int k = 0; k < GAMD_MAX_BOND; k++) flag = (a.bond[lc * GAMD_MAX_BOND + k] == ln) ? 1.f : flag;
+            }
+          }
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int k = ch * 32 + j;                 // feature column
+          float v = 0.f;
+          if (k == 0) v = ux;
+          else if (k == 1) v = uy;
+          else if (k == 2) v = uz;
+          else if (k == 3) v = dh;
+          else if (k < 4 + GAMD_NRBF) {
+            if (a.expand_edge) {
+              const float q = dh - sm.centers[k - 4];
+              // torch.exp(-40 * radial**2) (nn_module.py:261-263)
+              v = valid ? ex2_approx(-57.70780163555854f * (q * q)) : 0.f;
+            } else if (k == 4 && a.use_bond) {
+              v = flag;
+            }
+          } else if (k == 4 + GAMD_NRBF && a.use_bond && a.expand_edge) {
+            v = flag;
+          }
+          f[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {                // K step 2 ch + j: columns 16 (2 ch + j): [hi | lo]
+          uint32_t h[8], l[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) split_bf16(f[16 * j + 2 * q], f[16 * j + 2 * q + 1], h[q], l[q]);
+          tmem_st8(Hb + (2 * ch + j) * 16, h);
+          if (exact) tmem_st8(Hb + (2 * ch + j) * 16 + 8, l);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&sm.a_ready[g]);
+      }
+
+      // ---- stages 0 and 1: + bias, GELU, split -> next operand, in place (my 64 columns) ----
+#pragma unroll 1
+      for (int s = 0; s < 2; s++) {
+        mbar_wait(&sm.d_ready[g], d_par);
+        d_par ^= 1;
+        tc_fence_after();
+        Hb = tb + lane_base + sm.home[g] * 128u;
+        const uint32_t Dc = Hb + col0;
+        uint32_t vbuf[2][16];
+        tmem_ld16(Dc, vbuf[0]);
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          tmem_wait_ld();
+          if (cc < 3) tmem_ld16(Dc + (cc + 1) * 16, vbuf[(cc + 1) & 1]);
+          const uint32_t(&v)[16] = vbuf[cc & 1];
+          uint32_t h[8], l[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 b = lds128(bias_addr + (s * 128 + cc * 16 + j4 * 4) * 4);
+            split2(gelu_as2(add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y))), h[2 * j4], l[2 * j4]);
+            split2(gelu_as2(add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w))), h[2 * j4 + 1], l[2 * j4 + 1]);
+          }
+          tmem_st8(Dc + cc * 16, h);
+          if (exact) tmem_st8(Dc + cc * 16 + 8, l);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&sm.a_ready[g]);
+      }
+
+      // ---- stage 2: + bias, LayerNorm over the 128 columns (two warps per row exchange partial sums) ----
+      {
+        mbar_wait(&sm.d_ready[g], d_par);
+        d_par ^= 1;
+        tc_fence_after();
+        Hb = tb + lane_base + sm.home[g] * 128u;
+        const uint32_t Dc = Hb + col0;
+        float s1 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          uint32_t v[16];
+          tmem_ld16(Dc + cc * 16, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 b = lds128(bias_addr + (2 * 128 + cc * 16 + j4 * 4) * 4);
+            const f32x2 S = add2(add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y)),
+                                 add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w)));
+            float sa, sb;
+            unpk2(S, sa, sb);
+            s1 += sa + sb;
+          }
+        }
+        sm.xch[g][r][ch] = s1;
+        named_bar_sync(bar_id, 64);
+        const float mean = (sm.xch[g][r][0] + sm.xch[g][r][1]) * (1.f / 128.f);
+        named_bar_sync(bar_id, 64);
+        float s2 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          uint32_t v[16];
+          tmem_ld16(Dc + cc * 16, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 b = lds128(bias_addr + (2 * 128 + cc * 16 + j4 * 4) * 4);
+            const f32x2 NM = pk2(-mean, -mean);
+            const f32x2 D0 = add2(add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y)), NM);
+            const f32x2 D1 = add2(add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w)), NM);
+            const f32x2 Q = fma2(D1, D1, mul2(D0, D0));
+            float qa, qb;
+            unpk2(Q, qa, qb);
+            s2 += qa + qb;
+          }
+        }
+        sm.xch[g][r][ch] = s2;
+        named_bar_sync(bar_id, 64);
+        const float rstd = 1.f / sqrtf((sm.xch[g][r][0] + sm.xch[g][r][1]) * (1.f / 128.f) + 1e-5f);
+        uint8_t* blob = a.e_blob + (size_t)tile * 65536;
+        const uint32_t lnw_addr = smem_u32(&sm.ln_w[col0]), lnb_addr = smem_u32(&sm.ln_b[col0]);
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          uint32_t v[16];
+          tmem_ld16(Dc + cc * 16, v);
+          tmem_wait_ld();
+          uint32_t hh[8], ll[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 b = lds128(bias_addr + (2 * 128 + cc * 16 + j4 * 4) * 4);
+            const float4 w = lds128(lnw_addr + (cc * 16 + j4 * 4) * 4);
+            const float4 o = lds128(lnb_addr + (cc * 16 + j4 * 4) * 4);
+            const f32x2 NM = pk2(-mean, -mean), RS = pk2(rstd, rstd);
+            const f32x2 Y0 = fma2(mul2(add2(add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y)), NM), RS), pk2(w.x, w.y),
+                                  pk2(o.x, o.y));
+            const f32x2 Y1 = fma2(mul2(add2(add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w)), NM), RS),
+                                  pk2(w.z, w.w), pk2(o.z, o.w));
+            split2(Y0, hh[2 * j4], ll[2 * j4]);
+            split2(Y1, hh[2 * j4 + 1], ll[2 * j4 + 1]);
+          }
+          if (valid) {
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+              const int kc = (col0 + cc * 16 + half * 8) >> 3;    // 8-wide k-chunk index
+              *reinterpret_cast<uint4*>(blob + ((size_t)kc * 128 + r) * 16) =
+                  make_uint4(hh[half * 4], hh[half * 4 + 1], hh[half * 4 + 2], hh[half * 4 + 3]);
+              if (exact)
+                *reinterpret_cast<uint4*>(blob + 32768 + ((size_t)kc * 128 + r) * 16) =
+                    make_uint4(ll[half * 4], ll[half * 4 + 1], ll[half * 4 + 2], ll[half * 4 + 3]);
+            }
+          }
+        }
+        // the next tile's stage-0 operand overwrites columns [0, 64) of this block, part of which the OTHER column-half
+        // warp of my rows may still be reading: both halves of a row group leave the LayerNorm together
+        named_bar_sync(bar_id, 64);
+      }
+    }
+  } else if (warp == MMA_WARP3) {
+    // MMA issue: event loop over the three slots (see mp_tc3.cu); weights resident, so only the operands gate a GEMM
+    const uint32_t leader = elect_leader();
+    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    const int n_my_groups = blockIdx.x < ngroups ? (ngroups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int totalQ = 3 * n_my_groups;
+    int Qg[NSLOT3];
+    uint32_t a_par[NSLOT3], home[NSLOT3];
+#pragma unroll
+    for (int g = 0; g < NSLOT3; g++) {
+      Qg[g] = 0;
+      a_par[g] = 0;
+      home[g] = g;
+    }
+    uint32_t floating = NSLOT3;
+    int first = 0;
+    uint32_t spins = 0;
+    const uint32_t wbase = smem_u32(sm.w);
+    bool w_ready = false;
+    for (;;) {
+      bool done = true;
+#pragma unroll
+      for (int g = 0; g < NSLOT3; g++) done = done && Qg[g] >= totalQ;
+      if (done) break;
+      if (!w_ready) {
+        mbar_wait(&sm.w_full, 0);
+        w_ready = true;
+      }
+      bool progressed = false;
+      int pick = -1, best = NSLOT3;
+#pragma unroll
+      for (int g = 0; g < NSLOT3; g++) {
+        const int Q = Qg[g];
+        if (Q >= totalQ) continue;
+        const int grp = blockIdx.x + (Q / 3) * gridDim.x;
+        if (grp * NSLOT3 + g >= ntiles) {          // absent tile of the tail group
+          Qg[g] = totalQ;
+          progressed = true;
+          continue;
+        }
+        if (!__all_sync(0xffffffffu, mbar_test_wait(&sm.a_ready[g], a_par[g]))) continue;
+        int pr = g - first;
+        if (pr < 0) pr += NSLOT3;
+        if (pr < best) {
+          best = pr;
+          pick = g;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < NSLOT3; g++) {
+        if (g != pick) continue;
+        const int s = Qg[g] % 3;
+        a_par[g] ^= 1;
+        tc_fence_after();
+        const uint32_t off = s == 0 ? OFF_ENC0 : (s == 1 ? OFF_ENC2 : OFF_ENC4);
+        const uint32_t part = s == 0 ? W0 : W1;
+        const int nks = s == 0 ? 4 : 8;
+        const uint32_t d = tb + floating * 128u, ab = tb + home[g] * 128u;
+        if (leader) sm.home[g] = floating;
+        __threadfence_block();
+        const int passes = exact ? 3 : 1;
+        uint32_t accum = 0;
+        for (int p = 0; p < passes; p++) {
+          const uint32_t bb = wbase + off + (p == 2 ? part : 0);
+          const uint32_t aa = ab + (p == 1 ? 8u : 0u);
+          for (int ks = 0; ks < nks; ks++) {
+            umma_ts_elect(d, aa + ks * 16, umma_desc_sw128(bb + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, accum, leader);
+            accum = 1;
+          }
+        }
+        if (leader) umma_commit(&sm.d_ready[g]);
+        __syncwarp();
+        const uint32_t old_home = home[g];
+        home[g] = floating;
+        floating = old_home;
+        first = g + 1 == NSLOT3 ? 0 : g + 1;
+        Qg[g]++;
+        progressed = true;
+      }
+      if (progressed) spins = 0;
+      else if (++spins > (1u << 26)) __trap();
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0 && blockIdx.x < ngroups) {
+      mbar_arrive_expect_tx(&sm.w_full, W_TOTAL);
+      for (int i = 0; i < W_TOTAL / 8192; i++) bulk_g2s(sm.w + i * 8192, a.w_img + i * 8192, 8192, &sm.w_full);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP3) tmem_dealloc(tb, 512);
+}
+
 }  // namespace
 
 int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int atoms_per_frame,
@@ -426,7 +773,15 @@ int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig
   a.atoms_per_frame = atoms_per_frame;
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
   a.dynbox = mw.kind == GAMD_MODEL_DYNBOX ? 1 : 0;
-  k_edge_encode_tc<<<ctx->sm_count, THREADS, smem, st>>>(a);
+  if (ctx->enc_variant == 3) {
+    if (!(ctx->attr_mask & GAMD_ATTR_ENC_TC3)) {
+      GAMD_CUDA(cudaFuncSetAttribute(k_edge_encode_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemEnc3)));
+      ctx->attr_mask |= GAMD_ATTR_ENC_TC3;
+    }
+    k_edge_encode_tc3<<<ctx->sm_count, THREADS3, sizeof(SmemEnc3), st>>>(a);
+  } else {
+    k_edge_encode_tc<<<ctx->sm_count, THREADS, smem, st>>>(a);
+  }
   GAMD_LAUNCH_CHECK();
   return 0;
 }

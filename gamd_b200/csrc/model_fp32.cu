@@ -554,6 +554,7 @@ int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64
                 const float box[3], cudaStream_t st) {
   int rc = model_attrs(ctx);
   if (rc) return rc;
+  ctx->model_atoms = n_atoms;
   const ModelW& mw = ctx->mw;
   const int grid_edge = ctx->sm_count * 3;
   const int node_tiles = ceil_div(n_atoms, TM);

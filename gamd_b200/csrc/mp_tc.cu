@@ -567,7 +567,11 @@ int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which) {
   // GAMD_MP_VARIANT (read at gamd_create): 3 = three tiles in flight (mp_tc3.cu), 4 = the same without the commit wait
   if (ctx->mp_variant == 3 || ctx->mp_variant == 4) return mp_edge_tc3_launch(ctx, layer, st, which, ctx->mp_variant == 3);
   // 5 = CTA pairs (cta_group::2) with resident weights, three tiles in flight (mp_tc2cta.cu); 6 = without the commit wait
-  if (ctx->mp_variant == 5 || ctx->mp_variant == 6) return mp_edge_tc2_launch(ctx, layer, st, which, ctx->mp_variant == 5);
+  // launch-bound systems (at most a tile or two per SM: LJ-258, TIP3P-774) run the two-tile single-CTA kernel below: its
+  // tile chain is shorter (33 k cycles against 46 k), and with one tile per CTA only the chain length counts
+  const bool tiny = ctx->model_atoms > 0 && ctx->model_atoms <= ctx->mp_small_atoms;
+  if ((ctx->mp_variant == 5 || ctx->mp_variant == 6) && !tiny)
+    return mp_edge_tc2_launch(ctx, layer, st, which, ctx->mp_variant == 5);
   const size_t smem = sizeof(SmemTC) + 1024;
   if (!(ctx->attr_mask & GAMD_ATTR_MP_TC)) {
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

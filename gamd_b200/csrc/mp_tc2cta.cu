@@ -226,6 +226,29 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
       if (S == 1) issue_gather(c, cc + 2);
       continue;
     }
+    if (S == 3) {
+      // message = hn[src] * e_emb on packed fp32x2, parked (fp32) in my own accumulator columns until all four chunks
+      // are done.  Rows past the end of the edge list (tail of the last tile, phantom tiles) may hold anything: they
+      // follow the last valid row of their warp, so the in-order segmented sum never stores a sum that includes them.
+      uint32_t pr[16];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; j4++) {
+        const float4 b = lds128(c.bias_addr + (3 * 128 + cc * 16 + j4 * 4) * 4);
+        const float4 hv = lds128(grow + ((j4 ^ c.gswz) << 4));
+        const f32x2 M0 = mul2(add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y)), pk2(hv.x, hv.y));
+        const f32x2 M1 = mul2(add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w)), pk2(hv.z, hv.w));
+        float m0, m1, m2, m3;
+        unpk2(M0, m0, m1);
+        unpk2(M1, m2, m3);
+        pr[4 * j4] = __float_as_uint(m0);
+        pr[4 * j4 + 1] = __float_as_uint(m1);
+        pr[4 * j4 + 2] = __float_as_uint(m2);
+        pr[4 * j4 + 3] = __float_as_uint(m3);
+      }
+      tmem_st16(c.Dc + cc * 16, pr);
+      if (cc < 2) issue_gather(c, 4 + cc + 2);
+      continue;
+    }
     float x[16];
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {

@@ -14,6 +14,7 @@
 // The predicate is evaluated for every DIRECTED pair from its own centre, one IEEE rounding
 // per operation (no FMA contraction), so the edge set is bit-identical to oracle/neighbor.py.
 #include "common.cuh"
+#include <algorithm>
 #include <cstring>
 
 // ------------------------------------------------------------------------------------------
@@ -367,15 +368,10 @@ __device__ __forceinline__ int sweep_range(int lo, int hi, int s, const float4& 
 }
 
 template <bool WRITE, bool GENERAL>
-__global__ void __launch_bounds__(256) k_sweep(NbrParams p, const float4* __restrict__ pos,
-                                               const uint32_t* __restrict__ keys,
-                                               const int* __restrict__ cell_start, int* __restrict__ deg,
-                                               const int* __restrict__ row_ptr, int* __restrict__ col,
-                                               int* __restrict__ edst, int cap, int* __restrict__ err_flag,
-                                               const int* __restrict__ gate) {
-  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (s >= p.n_atoms || (gate && !*gate)) return;
+__device__ __forceinline__ void sweep_centre(int s, int lane, const NbrParams& p, const float4* __restrict__ pos,
+                                             const uint32_t* __restrict__ keys, const int* __restrict__ cell_start,
+                                             int* __restrict__ deg, const int* __restrict__ row_ptr, int* __restrict__ col,
+                                             int* __restrict__ edst, int cap, int* __restrict__ err_flag) {
   float4 pc = pos[s];
   int key = (int)keys[s];
   int frame = key / p.cells_per_frame;
@@ -420,6 +416,22 @@ __global__ void __launch_bounds__(256) k_sweep(NbrParams p, const float4* __rest
     }
   }
   if (!WRITE && lane == 0) deg[s] = cnt;
+}
+
+// one warp per centre, grid-stride (a bounded grid: a gated-off launch of the skin path must cost microseconds, not the
+// 0.27 ms that 125 000 empty CTAs take at 1 M atoms)
+template <bool WRITE, bool GENERAL>
+__global__ void __launch_bounds__(256) k_sweep(NbrParams p, const float4* __restrict__ pos,
+                                               const uint32_t* __restrict__ keys,
+                                               const int* __restrict__ cell_start, int* __restrict__ deg,
+                                               const int* __restrict__ row_ptr, int* __restrict__ col,
+                                               int* __restrict__ edst, int cap, int* __restrict__ err_flag,
+                                               const int* __restrict__ gate) {
+  if (gate && !*gate) return;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < p.n_atoms; s += warps)
+    sweep_centre<WRITE, GENERAL>(s, lane, p, pos, keys, cell_start, deg, row_ptr, col, edst, cap, err_flag);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,7 +531,7 @@ int nbr_sort_and_sweep(gamd_ctx* ctx, const NbrParams& p, const float* d_feat, c
                                                     ctx->inv_perm, ctx->cell_start, nullptr);
   GAMD_LAUNCH_CHECK();
   int cap = (int)ctx->cap_edges;
-  int blocks = ceil_div((int64_t)n * 32, 256);
+  int blocks = std::min(ceil_div((int64_t)n * 32, 256), ctx->sm_count * 32);
   bool general = (p.flags & GAMD_NBR_NOWRAP) != 0;
   if (general)
     k_sweep<false, true><<<blocks, 256, 0, st>>>(p, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg, nullptr,
@@ -559,99 +571,98 @@ struct SmallSmem {
   float4 pos[SMALL_MAX];
 };
 
-// FUSED: the frame's row offsets start at 0 and the kernel writes row_ptr / n_edges itself (n_frames == 1);
-// otherwise pass 0 (count: deg + masks to global) and pass 1 (fill from the masks) bracket the global scan
-template <int PASS, bool FUSED>
-__global__ void __launch_bounds__(SMALL_THREADS) k_nbr_small(const double* __restrict__ x, double scale, double bx,
-                                                             double by, double bz, NbrParams p,
-                                                             const float* __restrict__ feat, float4* __restrict__ pos_nbr,
-                                                             float4* __restrict__ pos_nbr_s, float4* __restrict__ pos_feat_s,
-                                                             int* __restrict__ perm, int* __restrict__ inv_perm,
-                                                             int* __restrict__ deg_g, int* __restrict__ row_ptr,
-                                                             uint32_t* __restrict__ gmask, int* __restrict__ col,
-                                                             int* __restrict__ edst, int cap, int* __restrict__ n_edges,
-                                                             int* __restrict__ err_flag) {
-  extern __shared__ __align__(16) unsigned char small_raw[];
-  SmallSmem& sm = *reinterpret_cast<SmallSmem*>(small_raw);
-  uint32_t* smask = reinterpret_cast<uint32_t*>(small_raw + sizeof(SmallSmem));   // FUSED: [n][words] ballot masks
+// pass 0: wrap + exact predicate.  grid = (frames, slices): a CTA loads its frame's positions into shared memory and
+// its 32 warps take the centres of one slice (one centre per warp and round); ballot masks and degrees go to global.
+__global__ void __launch_bounds__(SMALL_THREADS) k_nbr_small_count(const double* __restrict__ x, double scale, double bx,
+                                                                   double by, double bz, NbrParams p,
+                                                                   const float* __restrict__ feat, float4* __restrict__ pos_nbr,
+                                                                   float4* __restrict__ pos_nbr_s, float4* __restrict__ pos_feat_s,
+                                                                   int* __restrict__ perm, int* __restrict__ inv_perm,
+                                                                   int* __restrict__ deg_g, uint32_t* __restrict__ gmask) {
+  __shared__ float4 spos[SMALL_MAX];
   const int n = p.atoms_per_frame, words = (n + 31) >> 5;
   const int base = blockIdx.x * n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  if (PASS == 0) {
-    for (int i = tid; i < n; i += blockDim.x) {
-      const int g = base + i;
-      const double px = x[3 * g] * scale, py = x[3 * g + 1] * scale, pz = x[3 * g + 2] * scale;
-      const float wx = wrap_pos((float)px, p.box[0]), wy = wrap_pos((float)py, p.box[1]), wz = wrap_pos((float)pz, p.box[2]);
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int g = base + i;
+    const double px = x[3 * g] * scale, py = x[3 * g + 1] * scale, pz = x[3 * g + 2] * scale;
+    const float wx = wrap_pos((float)px, p.box[0]), wy = wrap_pos((float)py, p.box[1]), wz = wrap_pos((float)pz, p.box[2]);
+    const float4 pn = make_float4(wx, wy, wz, __int_as_float(g));
+    spos[i] = pn;
+    if (blockIdx.y == 0) {          // one slice publishes the frame's arrays
       double fx = fmod(px, bx), fy = fmod(py, by), fz = fmod(pz, bz);
       if (fx < 0.0) fx += bx;
       if (fy < 0.0) fy += by;
       if (fz < 0.0) fz += bz;
-      const float4 pn = make_float4(wx, wy, wz, __int_as_float(g));
-      sm.pos[i] = pn;
       pos_nbr[g] = pn;
       pos_nbr_s[g] = pn;
       pos_feat_s[g] = make_float4((float)fx, (float)fy, (float)fz, feat ? feat[g] : 0.f);
       perm[g] = g;
       inv_perm[g] = g;
     }
-  } else {
-    for (int i = tid; i < n; i += blockDim.x) sm.pos[i] = pos_nbr_s[base + i];
   }
   __syncthreads();
-  uint32_t* mask = FUSED ? smask : gmask + (size_t)base * words;
-  if (PASS == 0) {
-    for (int i = warp; i < n; i += nwarps) {
-      const float4 pc = sm.pos[i];
-      int cnt = 0;
-      for (int w = 0; w < words; w++) {
-        const int j = w * 32 + lane;
-        bool ok = false;
-        if (j < n) {
-          ok = pass_pred(pair_dr2<false>(pc, sm.pos[j], p), p);
-          if (j == i) ok = (p.flags & GAMD_NBR_SELF) != 0;
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) mask[(size_t)i * words + w] = m;
-        cnt += __popc(m);
+  const int per = (n + gridDim.y - 1) / gridDim.y;
+  const int lo = blockIdx.y * per, hi = min(lo + per, n);
+  for (int i = lo + warp; i < hi; i += nwarps) {
+    const float4 pc = spos[i];
+    int cnt = 0;
+    for (int w = 0; w < words; w++) {
+      const int j = w * 32 + lane;
+      bool ok = false;
+      if (j < n) {
+        ok = pass_pred(pair_dr2<false>(pc, spos[j], p), p);
+        if (j == i) ok = (p.flags & GAMD_NBR_SELF) != 0;
       }
-      if (lane == 0) {
-        sm.deg[i] = cnt;
-        deg_g[base + i] = cnt;
-      }
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) gmask[((size_t)base + i) * words + w] = m;
+      cnt += __popc(m);
     }
-    if (!FUSED) return;
-    __syncthreads();
-    // block-wide exclusive scan of deg[0..n) (n <= 1024 = one element per thread)
-    const int v = tid < n ? sm.deg[tid] : 0;
+    if (lane == 0) deg_g[base + i] = cnt;
+  }
+}
+
+// pass 1: CSR rows from the masks.  SINGLE: one frame - the CTA scans the degrees itself (n <= 1024 = one per thread) and
+// publishes row_ptr / n_edges; otherwise row_ptr comes from the global scan.
+template <bool SINGLE>
+__global__ void __launch_bounds__(SMALL_THREADS) k_nbr_small_fill(NbrParams p, const int* __restrict__ deg_g,
+                                                                  int* __restrict__ row_ptr, const uint32_t* __restrict__ gmask,
+                                                                  int* __restrict__ col, int* __restrict__ edst, int cap,
+                                                                  int* __restrict__ n_edges, int* __restrict__ err_flag) {
+  __shared__ int s_off[SMALL_MAX + 1];
+  __shared__ int s_warp[33];
+  const int n = p.atoms_per_frame, words = (n + 31) >> 5;
+  const int base = blockIdx.x * n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  if (SINGLE) {
+    const int v = tid < n ? deg_g[tid] : 0;
     int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    if (lane == 31) sm.warp_sums[warp] = inc;
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-      const int ws = lane < nwarps ? sm.warp_sums[lane] : 0;
+      const int ws = lane < nwarps ? s_warp[lane] : 0;
       int winc = ws;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, winc, o);
         if (lane >= o) winc += t;
       }
-      sm.warp_sums[lane] = winc - ws;
-      if (lane == 31) sm.warp_sums[32] = winc;
+      s_warp[lane] = winc - ws;
+      if (lane == 31) s_warp[32] = winc;
     }
     __syncthreads();
-    const int ex = inc - v + sm.warp_sums[warp];
-    const int total = sm.warp_sums[32];
-    __syncthreads();
+    const int ex = inc - v + s_warp[warp];
+    const int total = s_warp[32];
     if (tid < n) {
-      sm.deg[tid] = ex;
+      s_off[tid] = ex;
       row_ptr[tid] = ex;
     }
     if (tid == 0) {
-      sm.deg[n] = total;
       row_ptr[n] = total;
       if (total > cap) {          // publish an empty edge list (see k_nbr_guard)
         atomicOr(err_flag, 1);
@@ -664,12 +675,11 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_nbr_small(const double* __res
     __syncthreads();
     if (total > cap) return;
   }
-  // fill from the masks
   for (int i = warp; i < n; i += nwarps) {
-    int out = FUSED ? sm.deg[i] : row_ptr[base + i];
-    if (!FUSED && row_ptr[base + i + 1] > cap) continue;
+    int out = SINGLE ? s_off[i] : row_ptr[base + i];
+    if (!SINGLE && row_ptr[base + i + 1] > cap) continue;
     for (int w = 0; w < words; w++) {
-      const uint32_t m = mask[(size_t)i * words + w];
+      const uint32_t m = gmask[((size_t)base + i) * words + w];
       if ((m >> lane) & 1u) {
         const int dst = out + __popc(m & ((1u << lane) - 1u));
         col[dst] = base + w * 32 + lane;
@@ -685,38 +695,28 @@ int nbr_small_frames(gamd_ctx* ctx, const double* d_x, double scale, const doubl
                      const float* d_feat, cudaStream_t st) {
   const int n = p.atoms_per_frame, words = (n + 31) >> 5;
   const int cap = (int)ctx->cap_edges;
+  if ((int64_t)p.n_atoms * words > ctx->vl_cap) {
+    ctx->err = "mask scratch too small for the per-frame neighbor search";
+    return GAMD_ECAPACITY;
+  }
+  uint32_t* gm = reinterpret_cast<uint32_t*>(ctx->vl_cand);     // scratch: the skin path is off for small frames
+  // a single frame spreads its centres over enough CTAs to fill the machine's latency, many frames take one each
+  const int slices = p.n_frames == 1 ? (n + 31) / 32 : (p.n_frames < ctx->sm_count ? 4 : 1);
+  k_nbr_small_count<<<dim3(p.n_frames, slices), p.n_frames == 1 ? 1024 : 256, 0, st>>>(
+      d_x, scale, box64[0], box64[1], box64[2], p, d_feat, ctx->pos_nbr, ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm,
+      ctx->inv_perm, ctx->deg, gm);
+  GAMD_LAUNCH_CHECK();
   if (p.n_frames == 1) {
-    const size_t smem = sizeof(SmallSmem) + (size_t)n * words * 4;
-    if (!(ctx->attr_mask & GAMD_ATTR_NBR_SMALL)) {
-      GAMD_CUDA(cudaFuncSetAttribute(k_nbr_small<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(SmallSmem) + SMALL_MAX * (SMALL_MAX / 32) * 4)));
-      ctx->attr_mask |= GAMD_ATTR_NBR_SMALL;
-    }
-    k_nbr_small<0, true><<<1, SMALL_THREADS, smem, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, d_feat, ctx->pos_nbr,
-                                                         ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm, ctx->inv_perm, ctx->deg,
-                                                         ctx->row_ptr, nullptr, ctx->col_idx, ctx->edge_dst, cap,
-                                                         ctx->n_edges, ctx->err_flag);
+    k_nbr_small_fill<true><<<1, SMALL_THREADS, 0, st>>>(p, ctx->deg, ctx->row_ptr, gm, ctx->col_idx, ctx->edge_dst, cap,
+                                                        ctx->n_edges, ctx->err_flag);
     GAMD_LAUNCH_CHECK();
   } else {
-    if ((int64_t)p.n_atoms * words > ctx->vl_cap / 32 * 32) {
-      ctx->err = "mask scratch too small for the per-frame neighbor search";
-      return GAMD_ECAPACITY;
-    }
-    uint32_t* gm = reinterpret_cast<uint32_t*>(ctx->vl_cand);     // scratch: the skin path is off for small frames
-    const size_t smem = sizeof(SmallSmem);
-    k_nbr_small<0, false><<<p.n_frames, 256, smem, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, d_feat, ctx->pos_nbr,
-                                                         ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm, ctx->inv_perm, ctx->deg,
-                                                         ctx->row_ptr, gm, ctx->col_idx, ctx->edge_dst, cap, ctx->n_edges,
-                                                         ctx->err_flag);
-    GAMD_LAUNCH_CHECK();
     int rc = scan_with_total(ctx, ctx->deg, ctx->row_ptr, p.n_atoms, ctx->n_edges, st);
     if (rc) return rc;
     k_nbr_guard<<<1, 1, 0, st>>>(ctx->row_ptr, p.n_atoms, cap, ctx->n_edges, ctx->err_flag);
     GAMD_LAUNCH_CHECK();
-    k_nbr_small<1, false><<<p.n_frames, 256, smem, st>>>(d_x, scale, box64[0], box64[1], box64[2], p, d_feat, ctx->pos_nbr,
-                                                         ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm, ctx->inv_perm, ctx->deg,
-                                                         ctx->row_ptr, gm, ctx->col_idx, ctx->edge_dst, cap, ctx->n_edges,
-                                                         ctx->err_flag);
+    k_nbr_small_fill<false><<<p.n_frames, 256, 0, st>>>(p, ctx->deg, ctx->row_ptr, gm, ctx->col_idx, ctx->edge_dst, cap,
+                                                        ctx->n_edges, ctx->err_flag);
     GAMD_LAUNCH_CHECK();
   }
   ctx->last_nbr = p;
@@ -772,15 +772,17 @@ __global__ void k_vl_pad32(const int* __restrict__ deg, int n, int* __restrict__
 __global__ void k_vl_finish_rows(const int* __restrict__ deg, const int* __restrict__ cand_ptr, int n, int cap,
                                  int* __restrict__ cand, const float4* __restrict__ pos_nbr_s,
                                  float4* __restrict__ pos_ref, int* __restrict__ err_flag, const int* __restrict__ gate) {
-  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (s >= n || !*gate) return;
-  if (lane == 0) pos_ref[s] = pos_nbr_s[s];
-  const int b = cand_ptr[s], e = cand_ptr[s + 1], d = deg[s];
-  if (e > cap) {
-    if (lane == 0) atomicOr(err_flag, 4);
-    return;
+  const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+  if (!*gate) return;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    if (lane == 0) pos_ref[s] = pos_nbr_s[s];
+    const int b = cand_ptr[s], e = cand_ptr[s + 1], d = deg[s];
+    if (e > cap) {
+      if (lane == 0) atomicOr(err_flag, 4);
+      continue;
+    }
+    for (int k = b + d + lane; k < e; k += 32) cand[k] = -1;
   }
-  for (int k = b + d + lane; k < e; k += 32) cand[k] = -1;
 }
 
 __global__ void k_vl_clear(int* flag, unsigned long long* counters) {
@@ -792,49 +794,51 @@ __global__ void k_vl_clear(int* flag, unsigned long long* counters) {
 __global__ void __launch_bounds__(256) k_vl_count(NbrParams p, const float4* __restrict__ pos,
                                                   const int* __restrict__ cand_ptr, const int* __restrict__ cand,
                                                   uint32_t* __restrict__ vmask, int* __restrict__ deg) {
-  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (s >= p.n_atoms) return;
-  const float4 pc = pos[s];
-  if (__float_as_int(pc.w) >= p.n_centers) {
-    if (lane == 0) deg[s] = 0;
-    return;
-  }
-  const int b = cand_ptr[s], e = cand_ptr[s + 1];
-  int cnt = 0;
-  for (int k = b; k < e; k += 32) {
-    const int j = cand[k + lane];
-    bool ok = false;
-    if (j >= 0) {
-      ok = pass_pred(pair_dr2<false>(pc, pos[j], p), p);
-      if (j == s) ok = (p.flags & GAMD_NBR_SELF) != 0;
+  const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < p.n_atoms; s += warps) {
+    const float4 pc = pos[s];
+    if (__float_as_int(pc.w) >= p.n_centers) {
+      if (lane == 0) deg[s] = 0;
+      continue;
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) vmask[k >> 5] = m;
-    cnt += __popc(m);
+    const int b = cand_ptr[s], e = cand_ptr[s + 1];
+    int cnt = 0;
+    for (int k = b; k < e; k += 32) {
+      const int j = cand[k + lane];
+      bool ok = false;
+      if (j >= 0) {
+        ok = pass_pred(pair_dr2<false>(pc, pos[j], p), p);
+        if (j == s) ok = (p.flags & GAMD_NBR_SELF) != 0;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) vmask[k >> 5] = m;
+      cnt += __popc(m);
+    }
+    if (lane == 0) deg[s] = cnt;
   }
-  if (lane == 0) deg[s] = cnt;
 }
 
 __global__ void __launch_bounds__(256) k_vl_fill(int n, const int* __restrict__ cand_ptr, const int* __restrict__ cand,
                                                  const uint32_t* __restrict__ vmask, const int* __restrict__ row_ptr,
                                                  int* __restrict__ col, int* __restrict__ edst, int cap,
                                                  int* __restrict__ err_flag) {
-  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (s >= n) return;
-  int out = row_ptr[s];
-  if (row_ptr[s + 1] > cap) {
-    if (lane == 0 && row_ptr[s + 1] > row_ptr[s]) atomicOr(err_flag, 1);
-    return;
-  }
-  const int b = cand_ptr[s], e = cand_ptr[s + 1];
-  for (int k = b; k < e; k += 32) {
-    const uint32_t m = vmask[k >> 5];
-    if ((m >> lane) & 1u) {
-      const int dst = out + __popc(m & ((1u << lane) - 1u));
-      col[dst] = cand[k + lane];
-      edst[dst] = s;
+  const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    int out = row_ptr[s];
+    if (row_ptr[s + 1] > cap) {
+      if (lane == 0 && row_ptr[s + 1] > row_ptr[s]) atomicOr(err_flag, 1);
+      continue;
     }
-    out += __popc(m);
+    const int b = cand_ptr[s], e = cand_ptr[s + 1];
+    for (int k = b; k < e; k += 32) {
+      const uint32_t m = vmask[k >> 5];
+      if ((m >> lane) & 1u) {
+        const int dst = out + __popc(m & ((1u << lane) - 1u));
+        col[dst] = cand[k + lane];
+        edst[dst] = s;
+      }
+      out += __popc(m);
+    }
   }
 }
 
@@ -877,7 +881,7 @@ int nbr_step_verlet(gamd_ctx* ctx, const double* d_x, double scale, const double
                                                     ctx->pos_feat, d_feat, ctx->pos_nbr_s, ctx->pos_feat_s, ctx->perm,
                                                     ctx->inv_perm, ctx->cell_start, flag);
   GAMD_LAUNCH_CHECK();
-  const int blocks = ceil_div((int64_t)n * 32, 256);
+  const int blocks = std::min(ceil_div((int64_t)n * 32, 256), ctx->sm_count * 32);
   const int cap_c = (int)ctx->vl_cap;
   k_sweep<false, false><<<blocks, 256, 0, st>>>(pc, ctx->pos_nbr_s, ctx->keys[buf], ctx->cell_start, ctx->deg, nullptr,
                                                 nullptr, nullptr, cap_c, ctx->err_flag, flag);
