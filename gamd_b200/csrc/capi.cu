@@ -286,6 +286,7 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   ctx->desc = *desc;
   ctx->use_graphs = getenv("GAMD_NO_GRAPH") == nullptr;
   ctx->dbg_timeline = getenv("GAMD_TIMELINE") != nullptr;
+  if (const char* e = getenv("GAMD_WAIT_HINT_NS")) ctx->wait_hint_ns = atoi(e);
   ctx->dd_reserve_sms = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
   // message-passing edge kernel: 6 = CTA pairs (cta_group::2), resident weights, three tiles in flight (default);
   // 5 = the same with a commit wait between GEMMs; 3 / 4 = three tiles, single CTA; 0 = the round-1 two-tile kernel
@@ -559,7 +560,9 @@ int gamd_finalize_weights(gamd_ctx* ctx) {
         for (int n = 0; n < 128; n++) tb[(size_t)(l * 4 + s) * 128 + n] = b[n];
       }
     // the same matrices for the CTA-pair kernel (tcgen05 cta_group::2): CTA h of a pair holds rows n = 64 h .. 64 h + 63
-    // of B, so that a CTA's 128 KB (4 stages x [hi | lo] x 16 KB) are contiguous: [layer][half][stage][part]
+    // of B, so that a CTA's 128 KB (4 stages x [hi | lo] x 16 KB) are contiguous: [layer][half][stage][part].
+    // N-split kernel (GAMD_MP_VARIANT=7): the GEMM runs as two N = 64 halves, half q = output columns 64 q .. 64 q + 63
+    // with CTA h supplying columns 64 q + 32 h .. + 31 as rows 32 q .. 32 q + 31 of its image
     {
       const size_t part = 16384;
       std::vector<uint8_t> img2((size_t)d.conv_layer * 2 * 4 * 2 * part, 0);
@@ -567,7 +570,8 @@ int gamd_finalize_weights(gamd_ctx* ctx) {
         for (int s = 0; s < 4; s++) {
           const std::vector<float>& w = ctx->host_w["graph_conv.conv." + std::to_string(l) + "." + names[s] + ".weight"];
           for (int n = 0; n < 128; n++) {
-            const int half = n >> 6, nl = n & 63;
+            const bool nsplit = ctx->mp_variant == 7;
+            const int half = nsplit ? (n >> 5) & 1 : n >> 6, nl = nsplit ? (n >> 6) * 32 + (n & 31) : n & 63;
             uint8_t* hi = img2.data() + ((((size_t)l * 2 + half) * 4 + s) * 2 + 0) * part;
             uint8_t* lo = hi + part;
             for (int k = 0; k < 128; k++) {

@@ -123,6 +123,7 @@ struct gamd_ctx {
   // development switches read once at gamd_create (never on the launch path)
   bool dbg_timeline = false;
   int dd_reserve_sms = 0;
+  int wait_hint_ns = 0;   // GAMD_WAIT_HINT_NS: mbarrier try_wait suspend-time hint in the tensor kernels' epilogues
   int mp_variant = 0;
   int enc_variant = 3;         // edge encoder: 3 = three tiles in flight (in-place TMEM operands), 0 = two tiles
   int64_t model_atoms = 0;     // atoms of the forward pass in flight (model_begin)
@@ -196,7 +197,7 @@ int exclusive_scan_i32(gamd_ctx* ctx, const int* d_in, int* d_out, int64_t n, cu
 // which: -1 every tile; 0 / 1 only the interior / boundary tiles of the domain-decomposition split (ctx->tile_list)
 int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which = -1);
 int mp_edge_tc3_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war);
-int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war);
+int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war, bool nsplit);
 int node_update_tc_launch(gamd_ctx* ctx, int mode, int layer, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 int edge_encode_tc_launch(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int atoms_per_frame,
                           const float box[3], cudaStream_t st);

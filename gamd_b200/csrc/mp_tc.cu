@@ -570,8 +570,9 @@ int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which) {
   // launch-bound systems (at most a tile or two per SM: LJ-258, TIP3P-774) run the two-tile single-CTA kernel below: its
   // tile chain is shorter (33 k cycles against 46 k), and with one tile per CTA only the chain length counts
   const bool tiny = ctx->model_atoms > 0 && ctx->model_atoms <= ctx->mp_small_atoms;
-  if ((ctx->mp_variant == 5 || ctx->mp_variant == 6) && !tiny)
-    return mp_edge_tc2_launch(ctx, layer, st, which, ctx->mp_variant == 5);
+  // 7 = 6 with every GEMM issued as two N = 64 halves (separate commits: the epilogue starts on the first half)
+  if (ctx->mp_variant >= 5 && ctx->mp_variant <= 7 && !tiny)
+    return mp_edge_tc2_launch(ctx, layer, st, which, ctx->mp_variant == 5, ctx->mp_variant == 7);
   const size_t smem = sizeof(SmemTC) + 1024;
   if (!(ctx->attr_mask & GAMD_ATTR_MP_TC)) {
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

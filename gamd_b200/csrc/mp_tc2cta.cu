@@ -51,7 +51,8 @@ struct __align__(1024) SmemTC {
   uint8_t w[4][2][WPART];            // my half (64 rows) of every stage's B image: [stage][hi | lo]
   uint8_t gather[EPI_WARPS][2][GBUF];
   float bias[4][128];
-  uint64_t w_full, a_ready[NSLOT], d_ready[NSLOT];   // a_ready is used in the leader CTA only (16 warp arrivals)
+  uint64_t w_full, a_ready[NSLOT], d_ready[NSLOT][2];   // a_ready: leader CTA only (16 warp arrivals); d_ready[g][h]: N half h
+                                                         // of the slot's accumulator (N-split kernels; else [g][0] only)
   volatile uint32_t home[NSLOT];     // TMEM column block (0..3) holding the accumulator of the slot's GEMM in flight
   uint32_t tmem_base;
 };
@@ -66,6 +67,7 @@ struct MpTcArgs {
   float *agg, *part;
   const int *tile_list, *n_list;   // optional: process only these tiles (domain decomposition: interior / boundary)
   int exact;
+  uint32_t wait_hint_ns;   // suspend-time hint of the epilogue warps' accumulator waits (0 = plain poll loop)
   long long* dbg;   // development: clock64 timeline of CTA 0 (nullptr = off)
 };
 
@@ -104,8 +106,20 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem) : "memory");
 }
 
+// column offset (inside my warp's share of the 128 accumulator columns) of my chunk cc = 0..3.  Plain kernels: a warp
+// owns 64 consecutive columns.  N-split kernels issue every GEMM as two N = 64 halves with separate commits; a warp
+// owns 32 columns of EACH half (chunks 0, 1 in the first, 2, 3 in the second), so that its epilogue starts when the
+// first half has landed and runs beside the second half's MMAs.
+template <bool NSPLIT>
+__device__ __forceinline__ constexpr int coff(int cc) {
+  return NSPLIT ? (cc >> 1) * 64 + (cc & 1) * 16 : cc * 16;
+}
+
 // per-thread state of an epilogue thread for the tile it is working on
 struct EpiCtx {
+  uint64_t* d_bar1;             // N-split: barrier of the second accumulator half
+  uint32_t d_par1;              // its parity for the current stage
+  uint32_t wait_hint_ns;
   uint32_t Dc;                  // TMEM address: my lane quadrant, my 64-column half of my tile's current home block
   uint32_t gbuf[2];             // shared addresses of my warp's two gather staging buffers
   uint32_t grow_off;            // my row inside a staging buffer (lane * GROW)
@@ -124,8 +138,9 @@ struct EpiCtx {
 
 // gather #gi of the current tile: gi = 0..7 -> (array = gi<4 ? srcA : hn, 16-column chunk = gi&3);
 // 64 B of each of my warp's 32 neighbour rows, coalesced: 4 lanes per row, 8 rows per instruction
+template <bool NSPLIT>
 __device__ __forceinline__ void issue_gather(const EpiCtx& c, int gi) {
-  const float* base = (gi < 4 ? c.srcA : c.hn) + c.col0 + (gi & 3) * 16 + c.gl_col;
+  const float* base = (gi < 4 ? c.srcA : c.hn) + c.col0 + coff<NSPLIT>(gi & 3) + c.gl_col;
   const uint32_t dst = c.gbuf[gi & 1];
   __syncwarp();
 #pragma unroll
@@ -170,7 +185,7 @@ __device__ __forceinline__ void silu_split_pair(f32x2 X, uint32_t& hi, uint32_t&
 }
 
 // epilogue of GEMM stage S for my 64 columns (4 chunks of 16)
-template <int S, bool EXACT>
+template <int S, bool EXACT, bool NSPLIT>
 __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
   float4 dn[4];
   if (S == 1) {
@@ -183,7 +198,11 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
   for (int cc = 0; cc < 4; cc++) {
     // TMEM loads are pipelined one chunk ahead: wait for chunk cc, then put chunk cc+1 in flight
     tmem_wait_ld();
-    if (cc < 3) tmem_ld16(c.Dc + (cc + 1) * 16, vbuf[(cc + 1) & 1]);
+    if (NSPLIT && cc == 1) {       // chunks 2, 3 are in the second N half of the accumulator
+      mbar_wait_hint(c.d_bar1, c.d_par1, c.wait_hint_ns);
+      tc_fence_after();
+    }
+    if (cc < 3) tmem_ld16(c.Dc + coff<NSPLIT>(cc + 1), vbuf[(cc + 1) & 1]);
     const uint32_t(&v)[16] = vbuf[cc & 1];
     uint32_t grow = 0;
     float4 dc[4];
@@ -201,7 +220,7 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
         for (int i = 0; i < 4; i++) dc[i] = dn[i];
         if (cc < 3) {
 #pragma unroll
-          for (int i = 0; i < 4; i++) dn[i] = __ldg(c.dst_row + (cc + 1) * 4 + i);
+          for (int i = 0; i < 4; i++) dn[i] = __ldg(c.dst_row + coff<NSPLIT>(cc + 1) / 4 + i);
         }
       }
     }
@@ -210,7 +229,7 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
       uint32_t h[8], l[8];
 #pragma unroll
       for (int j4 = 0; j4 < 4; j4++) {
-        const float4 b = lds128(c.bias_addr + (S * 128 + cc * 16 + j4 * 4) * 4);
+        const float4 b = lds128(c.bias_addr + (S * 128 + coff<NSPLIT>(cc) + j4 * 4) * 4);
         f32x2 X0 = add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y));
         f32x2 X1 = add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w));
         if (S == 1) {
@@ -221,9 +240,9 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
         silu_split_pair(X0, h[2 * j4], l[2 * j4]);
         silu_split_pair(X1, h[2 * j4 + 1], l[2 * j4 + 1]);
       }
-      tmem_st8(c.Dc + cc * 16, h);        // in place over the accumulator chunk just read: [hi pairs | lo pairs]
-      tmem_st8(c.Dc + cc * 16 + 8, l);
-      if (S == 1) issue_gather(c, cc + 2);
+      tmem_st8(c.Dc + coff<NSPLIT>(cc), h);        // in place over the accumulator chunk just read: [hi pairs | lo pairs]
+      tmem_st8(c.Dc + coff<NSPLIT>(cc) + 8, l);
+      if (S == 1) issue_gather<NSPLIT>(c, cc + 2);
       continue;
     }
     if (S == 3) {
@@ -233,7 +252,7 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
       uint32_t pr[16];
 #pragma unroll
       for (int j4 = 0; j4 < 4; j4++) {
-        const float4 b = lds128(c.bias_addr + (3 * 128 + cc * 16 + j4 * 4) * 4);
+        const float4 b = lds128(c.bias_addr + (3 * 128 + coff<NSPLIT>(cc) + j4 * 4) * 4);
         const float4 hv = lds128(grow + ((j4 ^ c.gswz) << 4));
         const f32x2 M0 = mul2(add2(pk2u(v[4 * j4], v[4 * j4 + 1]), pk2(b.x, b.y)), pk2(hv.x, hv.y));
         const f32x2 M1 = mul2(add2(pk2u(v[4 * j4 + 2], v[4 * j4 + 3]), pk2(b.z, b.w)), pk2(hv.z, hv.w));
@@ -245,14 +264,14 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
         pr[4 * j4 + 2] = __float_as_uint(m2);
         pr[4 * j4 + 3] = __float_as_uint(m3);
       }
-      tmem_st16(c.Dc + cc * 16, pr);
-      if (cc < 2) issue_gather(c, 4 + cc + 2);
+      tmem_st16(c.Dc + coff<NSPLIT>(cc), pr);
+      if (cc < 2) issue_gather<NSPLIT>(c, 4 + cc + 2);
       continue;
     }
     float x[16];
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {
-      const float4 b = lds128(c.bias_addr + (S * 128 + cc * 16 + j4 * 4) * 4);
+      const float4 b = lds128(c.bias_addr + (S * 128 + coff<NSPLIT>(cc) + j4 * 4) * 4);
       x[4 * j4] = __uint_as_float(v[4 * j4]) + b.x;
       x[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
       x[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
@@ -273,14 +292,14 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
       if (EXACT) {
 #pragma unroll
         for (int j = 0; j < 8; j++) split_bf16(silu_fast(x[2 * j]), silu_fast(x[2 * j + 1]), h[j], l[j]);
-        tmem_st8(c.Dc + cc * 16, h);
-        tmem_st8(c.Dc + cc * 16 + 8, l);
+        tmem_st8(c.Dc + coff<NSPLIT>(cc), h);
+        tmem_st8(c.Dc + coff<NSPLIT>(cc) + 8, l);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; j++) h[j] = pack_bf16(silu_tanh(x[2 * j]), silu_tanh(x[2 * j + 1]));
-        tmem_st8(c.Dc + cc * 16, h);
+        tmem_st8(c.Dc + coff<NSPLIT>(cc), h);
       }
-      if (S == 1) issue_gather(c, cc + 2);
+      if (S == 1) issue_gather<NSPLIT>(c, cc + 2);
     } else {
       // message = hn[src] * e_emb; parked (fp32) in my own accumulator columns until all four chunks are done
       uint32_t pr[16];
@@ -292,8 +311,8 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
         pr[4 * j4 + 2] = __float_as_uint(c.valid ? x[4 * j4 + 2] * hv.z : 0.f);
         pr[4 * j4 + 3] = __float_as_uint(c.valid ? x[4 * j4 + 3] * hv.w : 0.f);
       }
-      tmem_st16(c.Dc + cc * 16, pr);
-      if (cc < 2) issue_gather(c, 4 + cc + 2);
+      tmem_st16(c.Dc + coff<NSPLIT>(cc), pr);
+      if (cc < 2) issue_gather<NSPLIT>(c, 4 + cc + 2);
     }
   }
   if (S == 3) {
@@ -306,8 +325,8 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
 #pragma unroll 1
     for (int p = 0; p < 2; p++) {
       uint32_t v0[16], v1[16];
-      tmem_ld16(c.Dc + p * 32, v0);
-      tmem_ld16(c.Dc + p * 32 + 16, v1);
+      tmem_ld16(c.Dc + coff<NSPLIT>(2 * p), v0);
+      tmem_ld16(c.Dc + coff<NSPLIT>(2 * p + 1), v1);
       tmem_wait_ld();
       __syncwarp();
 #pragma unroll
@@ -328,7 +347,7 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
           acc += t[j];
           if ((c.end_mask >> (jb + j)) & 1u) {
             const unsigned long long ptr = __shfl_sync(0xffffffffu, (unsigned long long)c.out_row, jb + j);
-            reinterpret_cast<float*>(ptr)[p * 32 + lane] = acc;
+            reinterpret_cast<float*>(ptr)[(NSPLIT ? p * 64 : p * 32) + lane] = acc;
             acc = 0.f;
           }
         }
@@ -338,7 +357,7 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
   }
 }
 
-template <bool SAFE_WAR>
+template <bool SAFE_WAR, bool NSPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edge_tc2(MpTcArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
   SmemTC& sm = *reinterpret_cast<SmemTC*>(raw);
@@ -360,7 +379,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
     mbar_init(&sm.w_full, 1);
     for (int g = 0; g < NSLOT; g++) {
       mbar_init(&sm.a_ready[g], 16);      // one arrival per epilogue warp of the slot, BOTH CTAs
-      mbar_init(&sm.d_ready[g], 1);
+      mbar_init(&sm.d_ready[g][0], 1);
+      mbar_init(&sm.d_ready[g][1], 1);
       sm.home[g] = g;
     }
     fence_barrier_init();
@@ -386,7 +406,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
     const int r = wq * 32 + lane;
     const bool exact = a.exact != 0;
     EpiCtx c;
-    c.col0 = ch * 64;
+    c.col0 = NSPLIT ? ch * 32 : ch * 64;
     const uint32_t lane_base = ((uint32_t)(wq * 32) << 16) + c.col0;
     c.Dc = tb + lane_base + g * 128;          // the slot's first home block is block g
     c.gbuf[0] = smem_u32(sm.gather[warp][0]);
@@ -405,7 +425,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
     c.srcA = a.srcA;
     c.hn = a.hn;
     const uint32_t a_bar = mapa_u32(smem_u32(&sm.a_ready[g]), 0);   // the LEADER's barrier (shared::cluster address)
-    uint64_t* const d_bar = &sm.d_ready[g];
+    uint64_t* const d_bar = &sm.d_ready[g][0];
+    c.d_bar1 = &sm.d_ready[g][1];
+    c.wait_hint_ns = a.wait_hint_ns;
     uint32_t d_par = 0;
     long long* dbg_rec = a.dbg ? a.dbg + (rank * 32 + warp) * 256 : nullptr;   // development timeline of cluster 0
     int dbg_n = 0;
@@ -428,10 +450,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
       c.valid = e < E;
       // everything this tile needs from global memory first (independent loads, one L2 latency for all of them):
       // my half of the e tile and the endpoints of my edge
-      const uint4* bh = reinterpret_cast<const uint4*>(a.e_blob + (size_t)tile * 65536) + (ch * 8) * 128 + r;
+      // 16-byte chunk i = 0..7 of my row's share of the e tile: K step (i >> 1) of my four, see coff()
+      const uint4* bh = reinterpret_cast<const uint4*>(a.e_blob + (size_t)tile * 65536) + (c.col0 / 8) * 128 + r;
+      auto chunk_of = [](int i) { return NSPLIT ? (i >> 2) * 8 + (i & 3) : i; };
       uint4 q[8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) q[i] = __ldg(bh + i * 128);
+      for (int i = 0; i < 8; i++) q[i] = __ldg(bh + chunk_of(i) * 128);
       c.src = 0;
       int dst = -1;
       if (c.valid) {
@@ -441,11 +465,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
       // the next tile of this slot: pull its e blob and edge endpoints into L2 while this tile is being processed
       next_tile = tile_of(sslot + NSLOT * ncl);
       if (next_tile >= 0 && next_tile != phantom && (lane & 7) == 0) {
-        const uint8_t* nb = a.e_blob + (size_t)next_tile * 65536 + ((size_t)(ch * 8) * 128 + r) * 16;
+        const uint8_t* nb = a.e_blob + (size_t)next_tile * 65536 + ((size_t)(c.col0 / 8) * 128 + r) * 16;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + i * 2048));
-          if (exact) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + 32768 + i * 2048));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + chunk_of(i) * 2048));
+          if (exact) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + 32768 + chunk_of(i) * 2048));
         }
         if (ch == 0) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(a.col + (size_t)next_tile * TILE + r));
@@ -453,8 +477,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
         }
       }
       c.dst_row = reinterpret_cast<const float4*>(a.dstA + (size_t)(dst < 0 ? 0 : dst) * 128 + c.col0);
-      issue_gather(c, 0);
-      issue_gather(c, 1);
+      issue_gather<NSPLIT>(c, 0);
+      issue_gather<NSPLIT>(c, 1);
 
       // ---- stage 0 operand: my half of the e tile -> my 64 columns of the home block, K step j at columns 16 j:
       //      [8 columns of bf16 hi pairs | 8 columns of lo pairs] (the layout every epilogue writes in place) ----
@@ -464,13 +488,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
           if (part == 1) {
             if (!exact) break;
 #pragma unroll
-            for (int i = 0; i < 8; i++) q[i] = __ldg(bh + 32768 / 16 + i * 128);
+            for (int i = 0; i < 8; i++) q[i] = __ldg(bh + 32768 / 16 + chunk_of(i) * 128);
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const uint32_t h[8] = {q[2 * j].x, q[2 * j].y, q[2 * j].z, q[2 * j].w,
                                    q[2 * j + 1].x, q[2 * j + 1].y, q[2 * j + 1].z, q[2 * j + 1].w};
-            tmem_st8(c.Dc + j * 16 + part * 8, h);
+            tmem_st8(c.Dc + coff<NSPLIT>(j) + part * 8, h);
           }
         }
         tmem_wait_st();
@@ -501,13 +525,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
       // times per tile)
 #define GAMD_STAGE(S)                              \
   if (dbg_on) dbg_rec[dbg_n++] = gtime();        \
-  mbar_wait(d_bar, d_par);                         \
+  mbar_wait_hint(d_bar, d_par, a.wait_hint_ns);    \
   d_par ^= 1;                                      \
   tc_fence_after();                                \
   c.Dc = tb + lane_base + sm.home[g] * 128u;       \
+  c.d_par1 = d_par ^ 1u;                           \
   if (dbg_on) dbg_rec[dbg_n++] = gtime();        \
-  if (exact) stage_epilogue<S, true>(c);           \
-  else stage_epilogue<S, false>(c);                \
+  if (exact) stage_epilogue<S, true, NSPLIT>(c);   \
+  else stage_epilogue<S, false, NSPLIT>(c);        \
   if (S < 3) {                                     \
     tmem_wait_st();                                \
     tc_fence_before();                             \
@@ -533,7 +558,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
     // lane (see tc_common.cuh: issuing from inside `if (lane == 0)` halves the MMA issue rate).
     {
       const uint32_t leader = elect_leader();
-      const uint32_t idesc = umma_idesc_bf16(256, 128);
+      const uint32_t idesc = umma_idesc_bf16(256, NSPLIT ? 64 : 128);
       const int n_my_groups = cid < ngroups ? (ngroups - 1 - cid) / ncl + 1 : 0;
       const int totalQ = 4 * n_my_groups;
       // per-slot state lives in registers: every loop over the slots is fully unrolled with static indices
@@ -612,27 +637,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
             fence_acq_rel_cluster();
           }
           __syncwarp();
-          // 24 (bf16x3) or 8 (bf16) MMAs, fully unrolled: per MMA only the TMEM column of A and the start-address field
-          // of the B descriptor change, both by compile-time constants
+          // 24 (bf16x3) or 8 (bf16) MMAs per N part, fully unrolled: per MMA only the TMEM column of A and the
+          // start-address field of the B descriptor change, both by compile-time constants.  N-split: two N = 64 GEMMs
+          // (rows 0-31 / 32-63 of each CTA's B image, accumulator columns 0-63 / 64-127), each with its own commit
           {
             const uint64_t dsc = umma_desc_sw128(bhi);
-            const uint32_t dhi = (uint32_t)(dsc >> 32), dlo_hi = (uint32_t)dsc, dlo_lo = dlo_hi + (WPART >> 4);
+            const uint32_t dhi = (uint32_t)(dsc >> 32);
 #pragma unroll
-            for (int ks = 0; ks < 8; ks++)     // A_hi * B_hi
-              umma_ts2_elect_lh(d, ab + ks * 16, dlo_hi + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, ks ? 1u : 0u, leader);
-            if (a.exact) {
+            for (int h = 0; h < (NSPLIT ? 2 : 1); h++) {
+              const uint32_t dlo_hi = (uint32_t)dsc + h * (4096 >> 4), dlo_lo = dlo_hi + (WPART >> 4);
+              const uint32_t dh = d + h * 64;
 #pragma unroll
-              for (int ks = 0; ks < 8; ks++)   // A_lo * B_hi
-                umma_ts2_elect_lh(d, ab + 8 + ks * 16, dlo_hi + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, 1u, leader);
+              for (int ks = 0; ks < 8; ks++)     // A_hi * B_hi
+                umma_ts2_elect_lh(dh, ab + ks * 16, dlo_hi + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, ks ? 1u : 0u, leader);
+              if (a.exact) {
 #pragma unroll
-              for (int ks = 0; ks < 8; ks++)   // A_hi * B_lo
-                umma_ts2_elect_lh(d, ab + ks * 16, dlo_lo + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, 1u, leader);
+                for (int ks = 0; ks < 8; ks++)   // A_lo * B_hi
+                  umma_ts2_elect_lh(dh, ab + 8 + ks * 16, dlo_hi + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, 1u, leader);
+#pragma unroll
+                for (int ks = 0; ks < 8; ks++)   // A_hi * B_lo
+                  umma_ts2_elect_lh(dh, ab + ks * 16, dlo_lo + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, 1u, leader);
+              }
+              if (leader) umma_commit2_mc(&sm.d_ready[g][h], (uint16_t)3);
             }
           }
-          if (leader) umma_commit2_mc(&sm.d_ready[g], (uint16_t)3);
           __syncwarp();
           if (dbg_on) dbg_rec[dbg_n++] = gtime();
-          last_bar = smem_u32(&sm.d_ready[g]);
+          last_bar = smem_u32(&sm.d_ready[g][NSPLIT ? 1 : 0]);
           last_par = (c_par_bits >> g) & 1u;
           c_par_bits ^= 1u << g;
           const uint32_t old_home = home[g];
@@ -658,11 +689,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
 }  // namespace
 
 // CTA pairs, resident weights, three tiles in flight per SM (see the header of this file)
-int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war) {
+int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war, bool nsplit) {
   const size_t smem = sizeof(SmemTC);
   if (!(ctx->attr_mask & GAMD_ATTR_MP_TC2)) {
-    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->attr_mask |= GAMD_ATTR_MP_TC2;
   }
   MpTcArgs a;
@@ -681,13 +713,16 @@ int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, boo
   a.tile_list = which >= 0 ? ctx->tile_list[which] : nullptr;
   a.n_list = which >= 0 ? ctx->tile_count + which : nullptr;
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
+  a.wait_hint_ns = (uint32_t)ctx->wait_hint_ns;
   a.dbg = (ctx->dbg_timeline && layer == 1) ? reinterpret_cast<long long*>(ctx->e_emb + (size_t)ctx->cap_edges * 128) : nullptr;
   // interior launch of a tile-split layer: optionally leave a few SMs to the halo exchange running beside it
   const int reserve = ctx->dd_reserve_sms;
   int grid = which == 0 && reserve > 0 && reserve < ctx->sm_count ? ctx->sm_count - reserve : ctx->sm_count;
   grid &= ~1;       // whole CTA pairs
-  if (safe_war) k_mp_edge_tc2<true><<<grid, THREADS, smem, st>>>(a);
-  else k_mp_edge_tc2<false><<<grid, THREADS, smem, st>>>(a);
+  // nsplit needs the N-split row order of the pair weight images (capi.cu builds them by ctx->mp_variant)
+  if (nsplit) k_mp_edge_tc2<false, true><<<grid, THREADS, smem, st>>>(a);
+  else if (safe_war) k_mp_edge_tc2<true, false><<<grid, THREADS, smem, st>>>(a);
+  else k_mp_edge_tc2<false, false><<<grid, THREADS, smem, st>>>(a);
   GAMD_LAUNCH_CHECK();
   return 0;
 }

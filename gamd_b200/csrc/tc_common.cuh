@@ -55,6 +55,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
+// wait that lets the hardware park the warp for up to hint_ns at a time (try_wait's optional suspend-time hint): a
+// parked warp issues nothing, a plain try_wait loop re-issues every few tens of cycles and competes with the warps
+// that have work.  hint_ns == 0 is the plain loop.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  if (hint_ns == 0) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 22); it++) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(hint_ns)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
 // ---- async proxy fences / bulk copy ------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP)
