@@ -104,6 +104,7 @@ SIGNATURES = {
     "gamd_peer_alloc": (c_int32, [c_void_p, c_int64, POINTER(c_void_p), c_void_p]),
     "gamd_peer_open": (c_int32, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "gamd_dd_push_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
+    "gamd_dd_arm_push": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
     "gamd_dd_push_bytes": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
     "gamd_dd_wait_flag": (c_int32, [c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
     "gamd_check_async_errors": (c_int32, [c_void_p, c_void_p]),
@@ -387,6 +388,19 @@ class Context:
     def dd_push_rows(self, local_idx_i32, remote_rows_ptr, remote_flag_ptr, seq):
         self._check(self.lib.gamd_dd_push_rows(self._h, _ptr(local_idx_i32), local_idx_i32.shape[0], remote_rows_ptr,
                                                remote_flag_ptr, int(seq), _stream()))
+
+    def dd_arm_push(self, slot_left, remote_left, slot_right, remote_right, n_own):
+        """the next dd_layer's node kernel also stores the rows of owned atoms with slot >= 0 into the neighbours'
+        buffers (int32 slot maps of n_own entries, -1 = not sent; None disables a side)."""
+        self._keep_push = (slot_left, slot_right)
+        self._check(self.lib.gamd_dd_arm_push(self._h, None if slot_left is None else _ptr(slot_left),
+                                              remote_left if slot_left is not None else None,
+                                              None if slot_right is None else _ptr(slot_right),
+                                              remote_right if slot_right is not None else None, int(n_own)))
+
+    def dd_signal(self, remote_flag_ptr, seq):
+        """publish `seq` to a neighbour's flag after everything queued on the stream so far (release, system scope)."""
+        self._check(self.lib.gamd_dd_push_rows(self._h, None, 0, None, remote_flag_ptr, int(seq), _stream()))
 
     def dd_push_bytes(self, src, remote_ptr, remote_flag_ptr, seq):
         self._check(self.lib.gamd_dd_push_bytes(self._h, _ptr(src), src.numel() * src.element_size(), remote_ptr,

@@ -1288,6 +1288,20 @@ int gamd_dd_push_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, floa
   return 0;
 }
 
+int gamd_dd_arm_push(gamd_ctx* ctx, const int32_t* d_slot_left, float* d_remote_rows_left, const int32_t* d_slot_right,
+                     float* d_remote_rows_right, int64_t n_own) {
+  if (!ctx || ctx->dd_n_loc <= 0 || n_own != ctx->dd_n_own) return GAMD_EINVAL;
+  if ((d_slot_left && !d_remote_rows_left) || (d_slot_right && !d_remote_rows_right)) return GAMD_EINVAL;
+  if (ctx->desc.precision == GAMD_PREC_FP32) return GAMD_EUNSUPPORTED;     // the tensor-core node kernel carries the push
+  ctx->dd_push_slot[0] = d_slot_left;
+  ctx->dd_push_slot[1] = d_slot_right;
+  ctx->dd_push_rows[0] = d_remote_rows_left;
+  ctx->dd_push_rows[1] = d_remote_rows_right;
+  ctx->dd_push_n = n_own;
+  ctx->dd_push_armed = d_slot_left || d_slot_right;
+  return 0;
+}
+
 int gamd_dd_push_bytes(gamd_ctx* ctx, const void* d_src, int64_t n_bytes, void* d_remote_dst,
                        unsigned long long* d_remote_flag, uint64_t seq, void* stream) {
   if (!ctx || n_bytes < 0 || (n_bytes & 15) || !d_remote_flag || (n_bytes > 0 && (!d_src || !d_remote_dst))) return GAMD_EINVAL;

@@ -123,6 +123,11 @@ struct gamd_ctx {
   // development switches read once at gamd_create (never on the launch path)
   bool dbg_timeline = false;
   int dd_reserve_sms = 0;
+  // fused halo push (gamd_dd_arm_push): consumed by the next node kernel launch of gamd_dd_layer / gamd_dd_layer_nodes
+  bool dd_push_armed = false;
+  const int* dd_push_slot[2] = {nullptr, nullptr};
+  float* dd_push_rows[2] = {nullptr, nullptr};
+  int64_t dd_push_n = 0;
   int wait_hint_ns = 0;   // GAMD_WAIT_HINT_NS: mbarrier try_wait suspend-time hint in the tensor kernels' epilogues
   int mp_variant = 0;
   int enc_variant = 3;         // edge encoder: 3 = three tiles in flight (in-place TMEM operands), 0 = two tiles

@@ -47,6 +47,11 @@ struct NodeTcArgs {
   const float* agg;
   float *h, *hn, *srcA, *dstA, *pd, *pred;
   int n_atoms, mode, exact;
+  // domain decomposition, fused halo push: rows of owned atoms that a neighbouring rank needs are ALSO stored straight
+  // into that rank's receive buffer over NVLink peer memory ([LN(h) | src_affine] = 256 floats per slot)
+  const int *perm, *push_slot[2];   // sorted row -> local atom; local atom -> slot in the left / right buffer or -1
+  float* push_rows[2];              // the neighbours' receive buffers (peer-mapped), nullptr = off
+  int push_n;                       // entries of the slot maps (owned atoms)
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -93,6 +98,8 @@ struct RowIO {
   int l_row, l_col;           // lane>>2, (lane&3)*4
   int row0;                   // first node row of my warp's 32 rows
   int n_atoms, col0;
+  int slot[2];                // my row's slot in the left / right neighbour's receive buffer (-1: not sent)
+  float* push_rows[2];
 };
 
 // 16 columns [col0 + cc*16, +16) of my warp's 32 rows of a row-major [n,128] fp32 matrix -> x[16] of my row
@@ -125,6 +132,24 @@ __device__ __forceinline__ void store_rows(const RowIO& io, float* __restrict__ 
     const int row = io.row0 + it * 8 + io.l_row;
     const float4 v = lds128(io.out_buf + io.l_off + it * 8 * GROW);
     if (row < io.n_atoms) *reinterpret_cast<float4*>(M + (size_t)row * 128 + io.col0 + cc * 16 + io.l_col) = v;
+  }
+}
+
+// the same store, plus the peer-memory copy of the rows a neighbouring rank needs: 64-byte segments at
+// remote[slot][part * 128 + column] (part 0 = LN(h), 1 = src_affine)
+__device__ __forceinline__ void store_rows_push(const RowIO& io, float* __restrict__ M, int cc, const float (&x)[16], int part) {
+  store_rows(io, M, cc, x);
+#pragma unroll
+  for (int side = 0; side < 2; side++) {
+    if (!io.push_rows[side]) continue;     // warp-uniform
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int slot = __shfl_sync(0xffffffffu, io.slot[side], it * 8 + io.l_row);
+      if (slot >= 0) {
+        const float4 v = lds128(io.out_buf + io.l_off + it * 8 * GROW);
+        *reinterpret_cast<float4*>(io.push_rows[side] + (size_t)slot * 256 + part * 128 + io.col0 + cc * 16 + io.l_col) = v;
+      }
+    }
   }
 }
 
@@ -191,6 +216,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
     io.l_off = (lane >> 2) * GROW + (lane & 3) * 16;
     io.n_atoms = a.n_atoms;
     io.col0 = col0;
+    io.slot[0] = io.slot[1] = -1;
+    io.push_rows[0] = a.push_rows[0];
+    io.push_rows[1] = a.push_rows[1];
     uint32_t d_par = 0;
     uint64_t* const a_bar = &sm.a_ready[g];
     uint64_t* const d_bar = &sm.d_ready[g];
@@ -259,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
           x[4 * j4 + 2] = (x[4 * j4 + 2] - mean) * rstd * w.z + o.z;
           x[4 * j4 + 3] = (x[4 * j4 + 3] - mean) * rstd * w.w + o.w;
         }
-        store_rows(io, a.hn, cc, x);
+        store_rows_push(io, a.hn, cc, x, 0);
         write_A(cc, x);
       }
     };
@@ -271,6 +299,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
       io.row0 = n0 + wq * 32;
       const int node = n0 + r;
       const bool valid = node < a.n_atoms;
+      if (a.push_rows[0] || a.push_rows[1]) {
+        const int lid = valid ? a.perm[node] : -1;
+#pragma unroll
+        for (int side = 0; side < 2; side++)
+          io.slot[side] = (lid >= 0 && a.push_rows[side] && lid < a.push_n) ? a.push_slot[side][lid] : -1;
+      }
 
       if (mode == MODE_FIRST) {
         // h0 = node_emb (LJ) or node_encoder(type) (water); stored to h and (fp32) into my D columns for the LN
@@ -366,7 +400,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
               const float4 b = bias_at(2 + k, cc, j4);
               x[4 * j4] += b.x; x[4 * j4 + 1] += b.y; x[4 * j4 + 2] += b.z; x[4 * j4 + 3] += b.w;
             }
-            store_rows(io, out, cc, x);
+            if (k == 0) store_rows_push(io, out, cc, x, 1);
+            else store_rows(io, out, cc, x);
           }
           // D of this slot is free again (A = hn stays): lets the MMA warp start the next affine / next tile
           if (k < 2) {
@@ -527,6 +562,15 @@ int node_update_tc_launch(gamd_ctx* ctx, int mode, int layer, const float4* pos_
   a.h = ctx->h; a.hn = ctx->hn; a.srcA = ctx->srcA; a.dstA = ctx->dstA; a.pd = ctx->pd; a.pred = ctx->pred;
   a.n_atoms = (int)n_atoms;
   a.mode = mode;
+  if (mode != MODE_LAST && ctx->dd_push_armed) {
+    a.perm = ctx->perm;
+    a.push_n = (int)ctx->dd_push_n;
+    for (int side = 0; side < 2; side++) {
+      a.push_slot[side] = ctx->dd_push_slot[side];
+      a.push_rows[side] = ctx->dd_push_slot[side] ? ctx->dd_push_rows[side] : nullptr;
+    }
+    ctx->dd_push_armed = false;     // one layer per arming
+  }
   // the node-sized GEMMs always run the 3-pass split: they cost ~4 % of the edge-sized ones, and single-pass bf16
   // there alone pushes the force error from 2e-3 to 1.3e-2
   a.exact = 1;

@@ -183,6 +183,24 @@ class PeerHalo:
         return (c.view(self._rows(self.base, par, 0), torch.float32, shape),
                 c.view(self._rows(self.base, par, 1), torch.float32, shape))
 
+    # fused form: the node kernel of the layer stores the rows into the neighbours' buffers itself
+    def arm_rows(self, slot_l, slot_r, n_own):
+        """call BEFORE the layer whose node update produces the rows (slot maps: local atom -> slot or -1)."""
+        self.seq_rows += 1
+        par, c = self.seq_rows & 1, self.ctx
+        c.dd_arm_push(slot_l, self._rows(self.left, par, 1), slot_r, self._rows(self.right, par, 0), n_own)
+
+    def finish_rows(self):
+        """call AFTER that layer: publish, wait for both neighbours -> (from_left, from_right) row buffers."""
+        seq, par, c = self.seq_rows, self.seq_rows & 1, self.ctx
+        c.dd_signal(self.left + 8 * 3, seq)
+        c.dd_signal(self.right + 8 * 2, seq)
+        c.dd_wait_flag(self.base + 8 * 2, seq)
+        c.dd_wait_flag(self.base + 8 * 3, seq)
+        shape = (self.cap, self.ROW_W)
+        return (c.view(self._rows(self.base, par, 0), torch.float32, shape),
+                c.view(self._rows(self.base, par, 1), torch.float32, shape))
+
 
 class CudaBackend:
     """Force evaluation on owned + halo atoms through the C ABI (``gamd_dd_*``)."""
@@ -229,6 +247,10 @@ class CudaBackend:
     def finish(self, f_own, v_own, mass_own, dt):
         self.ctx.dd_finish(f_own, v_own, mass_own, dt)
 
+    def check(self):
+        """device-side error flags (edge / candidate capacity, peer wait time-out) -> GamdError; synchronises."""
+        self.ctx.check_async_errors()
+
     def vv_first(self, x, v, f, mass, dt):
         """first half-kick + drift of the owned atoms in one kernel (hack_integrator.py:273-274)."""
         self.ctx.vv_first_half(x, v, f, mass, dt)
@@ -267,6 +289,15 @@ class SlabDomainMD:
         if (self.halo_cap is not None and x_nm.is_cuda and dist.is_initialized() and dist.get_backend() == "nccl"
                 and hasattr(backend, "ctx") and os.environ.get("GAMD_DD_PEER", "1") != "0"):
             self.peer = PeerHalo(backend.ctx, plan, self.halo_cap, 3 if feat is None else 4)
+        # fused push (GAMD_DD_FUSED_PUSH=1, tensor-core precisions): the node kernel stores the halo rows into the
+        # neighbours' buffers from its own epilogue instead of a separate pack kernel.  Measured neutral on 2 B200
+        # (the pack kernels' 0.25 ms/step move into the node kernel, which is itself memory-bound), so it is off by
+        # default; see profiles/experiments/README.md
+        self._slots = None
+        self.fused_push = False
+        if self.peer is not None and os.environ.get("GAMD_DD_FUSED_PUSH", "0") == "1":
+            from . import _capi
+            self.fused_push = backend.ctx.precision != _capi.PREC_FP32
 
     # ---- construction ------------------------------------------------------------------------------
     @staticmethod
@@ -302,6 +333,8 @@ class SlabDomainMD:
             moved = ((self.x - self._x_mig).norm(dim=1).max() * 1e7).long()
         mine = torch.stack([go_l.sum(), go_r.sum(), far.sum(), over.sum(), self._halo_max.max(), moved])
         table = _gather_stats(mine, p)
+        if hasattr(self.be, "check"):
+            self.be.check()            # the hand-over synchronises anyway: surface capacity / time-out flags here
         if self.halo_cap is not None:
             self._idx = None           # new halo lists at the next force evaluation
             if int(table[:, 5].max()) * 1e-6 > 0.5 * p.margin + 1e-9:
@@ -390,6 +423,15 @@ class SlabDomainMD:
             idx_l = torch.nonzero_static(to_l, size=cap, fill_value=-1).flatten()
             idx_r = torch.nonzero_static(to_r, size=cap, fill_value=-1).flatten()
             self._idx = (idx_l, idx_r, idx_l.clamp(min=0).to(torch.int32), idx_r.clamp(min=0).to(torch.int32))
+            self._slots = None
+            if self.peer is not None and self.fused_push:
+                # local atom -> slot in the neighbour's receive buffer (-1: not in that halo), for the node kernel
+                def slot_map(idx):
+                    sm = torch.full((pos.shape[0] + 1,), -1, dtype=torch.int32, device=pos.device)
+                    k = torch.arange(cap, dtype=torch.int32, device=pos.device)
+                    sm[torch.where(idx >= 0, idx, pos.shape[0])] = torch.where(idx >= 0, k, torch.full_like(k, -1))
+                    return sm[:-1].contiguous()
+                self._slots = (slot_map(idx_l), slot_map(idx_r))
             self._x_mig = self.x.clone()
             self._topo_changed = True
         idx_l, idx_r, i_l, i_r = self._idx
@@ -413,10 +455,15 @@ class SlabDomainMD:
         n_own = pos.shape[0]
         be.begin(pos_local, n_own, feat_local, stable=not self._topo_changed)
         self._topo_changed = False
+        fused = self.peer is not None and self._slots is not None
         for l in range(be.n_layers):
+            if fused and l + 1 < be.n_layers:
+                self.peer.arm_rows(self._slots[0], self._slots[1], n_own)   # this layer's node kernel pushes the rows
             be.layer(l)
             if l + 1 < be.n_layers:
-                if self.peer is not None:
+                if fused:
+                    r_l, r_r = self.peer.finish_rows()
+                elif self.peer is not None:
                     r_l, r_r = self.peer.exchange_rows(i_l, i_r)       # pack kernel writes into the neighbours' memory
                 else:
                     r_l, r_r = _exchange(be.pack(i_l), be.pack(i_r), p, cap, cap)

@@ -288,6 +288,11 @@ int gamd_dd_finish(gamd_ctx* ctx, double* d_force, double* d_v, const double* d_
  *   gamd_dd_push_rows  the rows [hn | src_affine(hn)] of the listed owned atoms are written by the pack kernel
  *                    STRAIGHT INTO the neighbour's buffer (no staging copy, no collective); a system-scope release
  *                    store of `seq` to the neighbour's flag follows in stream order
+ *   gamd_dd_arm_push   FUSED form of the above: the next gamd_dd_layer / gamd_dd_layer_nodes call stores the rows of the
+ *                    owned atoms with d_slot_left[i] / d_slot_right[i] >= 0 (i = local atom index < n_own) into slot
+ *                    d_slot_*[i] of the left / right neighbour's buffer FROM THE NODE KERNEL'S EPILOGUE, as it produces
+ *                    them (no pack kernel, the transfer runs under the kernel's own GEMMs); either side may be NULL.
+ *                    The caller then publishes with gamd_dd_push_rows(ctx, NULL, 0, NULL, flag, seq, stream)
  *   gamd_dd_push_bytes the same for a plain device buffer (halo positions); n_bytes must be a multiple of 16
  *   gamd_dd_wait_flag  stream-ordered wait until this rank's own flag has reached `seq` (bounded: a neighbour that never
  *                    delivers raises GAMD_ESTATE at the next gamd_check_async_errors instead of hanging the GPU) */
@@ -295,6 +300,8 @@ int gamd_peer_alloc(gamd_ctx* ctx, int64_t n_bytes, void** d_ptr, uint8_t h_hand
 int gamd_peer_open(gamd_ctx* ctx, const uint8_t h_handle[64], void** d_ptr);
 int gamd_dd_push_rows(gamd_ctx* ctx, const int32_t* d_local_idx, int64_t n, float* d_remote_rows,
                       unsigned long long* d_remote_flag, uint64_t seq, void* stream);
+int gamd_dd_arm_push(gamd_ctx* ctx, const int32_t* d_slot_left, float* d_remote_rows_left, const int32_t* d_slot_right,
+                     float* d_remote_rows_right, int64_t n_own);
 int gamd_dd_push_bytes(gamd_ctx* ctx, const void* d_src, int64_t n_bytes, void* d_remote_dst,
                        unsigned long long* d_remote_flag, uint64_t seq, void* stream);
 int gamd_dd_wait_flag(gamd_ctx* ctx, const unsigned long long* d_flag, uint64_t seq, void* stream);

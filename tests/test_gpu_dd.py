@@ -125,13 +125,15 @@ def test_slab_md_split_layers_equals_single_domain():
     assert abs(ret["ke"] - ke_ref) / ke_ref <= 1e-6
 
 
-@pytest.mark.parametrize("world,cap", [(2, 2200), (3, 1500)])
-def test_slab_md_fixed_capacity_halo_equals_single_domain(world, cap):
+@pytest.mark.parametrize("world,cap,fused", [(2, 2200, "0"), (3, 1500, "0"), (2, 2200, "1")])
+def test_slab_md_fixed_capacity_halo_equals_single_domain(world, cap, fused, monkeypatch):
     """lazy hand-over, FIXED-size halo messages (unused slots NaN-padded): the steps between hand-overs run without
     any host synchronisation and give the same trajectory as one domain.  With one GPU per rank (gpurun --gpus N) the
     halo travels by direct peer-memory writes (dist.PeerHalo: gamd_dd_push_rows / _push_bytes / _wait_flag over CUDA
-    IPC), otherwise (ranks sharing a GPU) through gloo."""
+    IPC), otherwise (ranks sharing a GPU) through gloo.  fused = "1": the halo rows are stored into the neighbours'
+    buffers by the node kernel's epilogue (gamd_dd_arm_push) instead of a pack kernel."""
     from gamd_b200 import _capi
+    monkeypatch.setenv("GAMD_DD_FUSED_PUSH", fused)          # inherited by the spawned ranks
     f_ref, x_ref, ke_ref = _reference(_capi.PREC_BF16X3)
     mgr = mp.Manager()
     ret = mgr.dict()
