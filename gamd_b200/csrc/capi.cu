@@ -287,10 +287,11 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   ctx->use_graphs = getenv("GAMD_NO_GRAPH") == nullptr;
   ctx->dbg_timeline = getenv("GAMD_TIMELINE") != nullptr;
   if (const char* e = getenv("GAMD_WAIT_HINT_NS")) ctx->wait_hint_ns = atoi(e);
+  if (const char* e = getenv("GAMD_MP_ROW_PREFETCH")) ctx->mp_row_prefetch = atoi(e);
   ctx->dd_reserve_sms = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
   // message-passing edge kernel: 6 = CTA pairs (cta_group::2), resident weights, three tiles in flight (default);
   // 5 = the same with a commit wait between GEMMs; 3 / 4 = three tiles, single CTA; 0 = the round-1 two-tile kernel
-  ctx->mp_variant = getenv("GAMD_MP_VARIANT") ? atoi(getenv("GAMD_MP_VARIANT")) : 6;
+  ctx->mp_variant = getenv("GAMD_MP_VARIANT") ? atoi(getenv("GAMD_MP_VARIANT")) : 8;
   // neighbor candidate reuse: skin as a fraction of the cutoff (reference: 1/6); GAMD_NBR_SKIN=0 rebuilds every step
   ctx->vl_skin_frac = getenv("GAMD_NBR_SKIN") ? (float)atof(getenv("GAMD_NBR_SKIN")) : (1.f / 6.f);
   if (getenv("GAMD_NBR_SKIN_MIN_ATOMS")) ctx->vl_min_atoms = atoll(getenv("GAMD_NBR_SKIN_MIN_ATOMS"));

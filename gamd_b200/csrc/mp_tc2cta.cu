@@ -24,8 +24,8 @@
 // leader's MMA warp publishes it in both CTAs' shared memory before the commit); the old home is the next floating
 // block.  The leader CTA (cluster rank 0) issues every MMA for the pair; the epilogue threads of both CTAs arrive on
 // the leader's a_ready barrier (cluster-scope release), commits are multicast to both CTAs' d_ready barriers.
-// CTA = 26 warps (72 registers): 24 epilogue warps (thread = edge row; 8 warps per tile = 4 TMEM lane quadrants x 2
-// column halves), 1 MMA-issue warp, 1 weight-loader warp.  Neighbour features are gathered with coalesced cp.async
+// CTA = 25 warps (80 registers): 24 epilogue warps (thread = edge row; 8 warps per tile = 4 TMEM lane quadrants x 2
+// column halves) and 1 MMA-issue warp, which also fetches the weights once.  Neighbour features are gathered with coalesced cp.async
 // into per-warp XOR-swizzled staging rows (no padding: 96 KB); the final
 // segmented sum walks the receiver-sorted rows in order (messages transposed through the staging tile, lane =
 // feature column) - no atomics, deterministic; rows that straddle a 32-edge block go to the `part` side buffer
@@ -44,8 +44,8 @@ constexpr int NSLOT = 3;             // tiles in flight
 constexpr int GROW = 64;             // staging row stride in bytes (un-padded; 16-byte chunks XOR-swizzled)
 constexpr int GBUF = 32 * GROW;      // one staging buffer: 32 rows x 64 B
 constexpr int EPI_WARPS = 8 * NSLOT; // tiles in flight x 4 lane quadrants x 2 column halves
-constexpr int MMA_WARP = EPI_WARPS;   // warp EPI_WARPS + 1 is the weight producer
-constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int MMA_WARP = EPI_WARPS;   // also loads the weights once at the start
+constexpr int THREADS = (EPI_WARPS + 1) * 32;   // 800 threads: an 80-register budget (26 warps would cap it at 72)
 
 struct __align__(1024) SmemTC {
   uint8_t w[4][2][WPART];            // my half (64 rows) of every stage's B image: [stage][hi | lo]
@@ -67,6 +67,7 @@ struct MpTcArgs {
   float *agg, *part;
   const int *tile_list, *n_list;   // optional: process only these tiles (domain decomposition: interior / boundary)
   int exact;
+  int row_prefetch;        // L2 prefetch of the tile's sender rows at tile start (GAMD_MP_ROW_PREFETCH)
   uint32_t wait_hint_ns;   // suspend-time hint of the epilogue warps' accumulator waits (0 = plain poll loop)
   long long* dbg;   // development: clock64 timeline of CTA 0 (nullptr = off)
 };
@@ -357,7 +358,7 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
   }
 }
 
-template <bool SAFE_WAR, bool NSPLIT>
+template <bool SAFE_WAR, bool NSPLIT, bool SETUP1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edge_tc2(MpTcArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
   SmemTC& sm = *reinterpret_cast<SmemTC*>(raw);
@@ -388,7 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
   for (int i = tid; i < 4 * 128; i += THREADS) (&sm.bias[0][0])[i] = a.bias[i];
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP + 1 && lane == 0) {
+  if (warp == MMA_WARP && lane == 0) {
     // my half of the layer's weights, resident for the whole kernel
     mbar_arrive_expect_tx(&sm.w_full, WTOTAL);
     const uint8_t* src = a.w_img + (size_t)rank * WTOTAL;
@@ -448,19 +449,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
       const int e0 = tile * TILE;
       const int e = e0 + r;
       c.valid = e < E;
-      // everything this tile needs from global memory first (independent loads, one L2 latency for all of them):
-      // my half of the e tile and the endpoints of my edge
       // 16-byte chunk i = 0..7 of my row's share of the e tile: K step (i >> 1) of my four, see coff()
       const uint4* bh = reinterpret_cast<const uint4*>(a.e_blob + (size_t)tile * 65536) + (c.col0 / 8) * 128 + r;
       auto chunk_of = [](int i) { return NSPLIT ? (i >> 2) * 8 + (i & 3) : i; };
-      uint4 q[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) q[i] = __ldg(bh + chunk_of(i) * 128);
-      c.src = 0;
       int dst = -1;
-      if (c.valid) {
-        c.src = __ldg(a.col + e);
-        dst = __ldg(a.edst + e);
+      c.src = 0;
+      if (SETUP1) {
+        // ---- stage 0 operand in ONE L2 round trip: the hi part of my share travels by cp.async through my warp's
+        // staging rows (idle until the first gather), the lo part through registers, both in flight together; the
+        // A-ready arrive comes before anything else the tile needs (endpoints, gathers, prefetches) ----
+        const uint32_t hrow = c.gbuf[0] + lane * 16;           // chunk-major: chunk i of lane l at 512 i + 16 l (4 KB)
+        __syncwarp();                                          // the previous tile's segmented sum read these rows
+#pragma unroll
+        for (int i = 0; i < 8; i++) cp_async16s(hrow + i * 512, bh + chunk_of(i) * 128);
+        cp_async_commit();
+        auto hi_from_staging = [&](int j) {
+          const float4 u0 = lds128(hrow + (2 * j) * 512);
+          const float4 u1 = lds128(hrow + (2 * j + 1) * 512);
+          const uint32_t h[8] = {__float_as_uint(u0.x), __float_as_uint(u0.y), __float_as_uint(u0.z), __float_as_uint(u0.w),
+                                 __float_as_uint(u1.x), __float_as_uint(u1.y), __float_as_uint(u1.z), __float_as_uint(u1.w)};
+          tmem_st8(c.Dc + coff<NSPLIT>(j), h);
+        };
+        if (c.valid) {
+          c.src = __ldg(a.col + e);
+          dst = __ldg(a.edst + e);
+        }
+        if (exact) {
+          uint4 ql[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) ql[i] = __ldg(bh + 32768 / 16 + chunk_of(i) * 128);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t l[8] = {ql[2 * j].x, ql[2 * j].y, ql[2 * j].z, ql[2 * j].w,
+                                   ql[2 * j + 1].x, ql[2 * j + 1].y, ql[2 * j + 1].z, ql[2 * j + 1].w};
+            tmem_st8(c.Dc + coff<NSPLIT>(j) + 8, l);
+          }
+        }
+        cp_async_wait<0>();               // my own row: no other lane's copy is read
+#pragma unroll
+        for (int j = 0; j < 4; j++) hi_from_staging(j);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(a_bar);
+      }
+      uint4 q[8];
+      if (!SETUP1) {
+        // everything this tile needs from global memory first (independent loads, one L2 latency for all of them):
+        // my half of the e tile and the endpoints of my edge
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = __ldg(bh + chunk_of(i) * 128);
+        if (c.valid) {
+          c.src = __ldg(a.col + e);
+          dst = __ldg(a.edst + e);
+        }
       }
       // the next tile of this slot: pull its e blob and edge endpoints into L2 while this tile is being processed
       next_tile = tile_of(sslot + NSLOT * ncl);
@@ -477,12 +519,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
         }
       }
       c.dst_row = reinterpret_cast<const float4*>(a.dstA + (size_t)(dst < 0 ? 0 : dst) * 128 + c.col0);
-      issue_gather<NSPLIT>(c, 0);
+      issue_gather<NSPLIT>(c, 0);        // (starts with a warp barrier: the staging rows are free again)
       issue_gather<NSPLIT>(c, 1);
+      if (a.row_prefetch && !NSPLIT) {
+        // gathers 2, 3 (src_affine) and 6, 7 (hn) are issued only one chunk before they are consumed - two staging
+        // buffers per warp - and a sender row's first touch comes from DRAM: pull my sender's 256 B of both arrays
+        // into L2 now, stages ahead (no registers, no staging)
+        const char* ps = reinterpret_cast<const char*>(a.srcA + (size_t)c.src * 128 + c.col0);
+        const char* ph = reinterpret_cast<const char*>(a.hn + (size_t)c.src * 128 + c.col0);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ph));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ph + 128));
+        if (a.row_prefetch > 1) {      // ... and my receiver's dst_affine half row (consumed in stage 1)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(c.dst_row)));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(c.dst_row) + 128));
+        }
+      }
 
-      // ---- stage 0 operand: my half of the e tile -> my 64 columns of the home block, K step j at columns 16 j:
-      //      [8 columns of bf16 hi pairs | 8 columns of lo pairs] (the layout every epilogue writes in place) ----
-      {
+      if (!SETUP1) {
+        // ---- stage 0 operand: my half of the e tile -> my 64 columns of the home block, K step j at columns 16 j:
+        //      [8 columns of bf16 hi pairs | 8 columns of lo pairs] (the layout every epilogue writes in place) ----
 #pragma unroll
         for (int part = 0; part < 2; part++) {
           if (part == 1) {
@@ -692,9 +749,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
 int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, bool safe_war, bool nsplit) {
   const size_t smem = sizeof(SmemTC);
   if (!(ctx->attr_mask & GAMD_ATTR_MP_TC2)) {
-    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->attr_mask |= GAMD_ATTR_MP_TC2;
   }
   MpTcArgs a;
@@ -714,15 +772,17 @@ int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, boo
   a.n_list = which >= 0 ? ctx->tile_count + which : nullptr;
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
   a.wait_hint_ns = (uint32_t)ctx->wait_hint_ns;
+  a.row_prefetch = ctx->mp_row_prefetch;
   a.dbg = (ctx->dbg_timeline && layer == 1) ? reinterpret_cast<long long*>(ctx->e_emb + (size_t)ctx->cap_edges * 128) : nullptr;
   // interior launch of a tile-split layer: optionally leave a few SMs to the halo exchange running beside it
   const int reserve = ctx->dd_reserve_sms;
   int grid = which == 0 && reserve > 0 && reserve < ctx->sm_count ? ctx->sm_count - reserve : ctx->sm_count;
   grid &= ~1;       // whole CTA pairs
   // nsplit needs the N-split row order of the pair weight images (capi.cu builds them by ctx->mp_variant)
-  if (nsplit) k_mp_edge_tc2<false, true><<<grid, THREADS, smem, st>>>(a);
-  else if (safe_war) k_mp_edge_tc2<true, false><<<grid, THREADS, smem, st>>>(a);
-  else k_mp_edge_tc2<false, false><<<grid, THREADS, smem, st>>>(a);
+  if (ctx->mp_variant == 8) k_mp_edge_tc2<false, false, true><<<grid, THREADS, smem, st>>>(a);
+  else if (nsplit) k_mp_edge_tc2<false, true, false><<<grid, THREADS, smem, st>>>(a);
+  else if (safe_war) k_mp_edge_tc2<true, false, false><<<grid, THREADS, smem, st>>>(a);
+  else k_mp_edge_tc2<false, false, false><<<grid, THREADS, smem, st>>>(a);
   GAMD_LAUNCH_CHECK();
   return 0;
 }
