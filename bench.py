@@ -47,7 +47,10 @@ WORKLOADS = {
 }
 FIX = os.path.join(ROOT, "tests", "golden", "fixtures")
 DT = 0.002  # ps (test_nosehoover.py:29)
-DD_MIGRATE_EVERY, DD_MARGIN = 8, 0.8   # domain decomposition: atom hand-over interval (steps), halo margin (A)
+# domain decomposition: atom hand-over interval (steps), halo margin (A); the largest displacement between two
+# hand-overs is checked against margin / 2 at run time
+DD_MIGRATE_EVERY = int(os.environ.get("GAMD_DD_MIGRATE_EVERY", "8"))
+DD_MARGIN = float(os.environ.get("GAMD_DD_MARGIN", "0.8"))
 
 
 def build_system(name, seed=42):

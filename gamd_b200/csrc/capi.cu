@@ -287,6 +287,8 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   ctx->use_graphs = getenv("GAMD_NO_GRAPH") == nullptr;
   ctx->dbg_timeline = getenv("GAMD_TIMELINE") != nullptr;
   if (const char* e = getenv("GAMD_WAIT_HINT_NS")) ctx->wait_hint_ns = atoi(e);
+  // GAMD_WAIT_SLEEP_NS: poll the accumulator barrier with __nanosleep(ns) between attempts instead
+  if (const char* e = getenv("GAMD_WAIT_SLEEP_NS")) ctx->wait_hint_ns = (int)(0x80000000u | (uint32_t)(atoi(e) & 0xffff));
   if (const char* e = getenv("GAMD_MP_ROW_PREFETCH")) ctx->mp_row_prefetch = atoi(e);
   ctx->dd_reserve_sms = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
   // message-passing edge kernel: 6 = CTA pairs (cta_group::2), resident weights, three tiles in flight (default);

@@ -63,6 +63,14 @@ __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, u
     mbar_wait(bar, parity);
     return;
   }
+  if (hint_ns & 0x80000000u) {      // poll with a sleep of (hint_ns & 0xffff) ns between attempts
+    const uint32_t ns = hint_ns & 0xffffu;
+    for (uint32_t it = 0; it < (1u << 24); it++) {
+      if (mbar_try_wait(bar, parity)) return;
+      __nanosleep(ns);
+    }
+    __trap();
+  }
   const uint32_t addr = smem_u32(bar);
   for (uint32_t it = 0; it < (1u << 22); it++) {
     uint32_t ok;
