@@ -122,4 +122,6 @@ def test_nve_trace_fixture_is_the_oracle(golden_dir, fixtures_dir):
     m = np.full(258, 39.9)
     ff = omd.OracleForceField(random_state_dict(0, 5.2, 1.5, kind="lj"), "lj", 27.27, 7.5, sc["mean"], sc["var"])
     _, _, _, trace = omd.run_nve(ff, pos / 10.0, maxwell_boltzmann(m, 100.0, 1234), m, 0.002, 40)
-    np.testing.assert_allclose(trace[:, 1], ko[:40], rtol=1e-9)
+    # the oracle's fp32 GEMMs run on torch CPU kernels whose summation order depends on the host's vector width /
+    # thread count: 1e-9 held on the machine that wrote the fixture, another host measured 1.15e-9
+    np.testing.assert_allclose(trace[:, 1], ko[:40], rtol=1e-7)
