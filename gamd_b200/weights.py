@@ -15,10 +15,12 @@ N_RBF = 40  # RBFExpansion(high=1, gap=0.025) -> ceil(1/0.025) centres (nn_modul
 
 
 def param_shapes(kind="lj", encoding_size=128, hidden_dim=128, edge_embedding_dim=128,
-                 conv_layer=4, in_feats=1, use_bond=None, expand_edge=True):
+                 conv_layer=4, in_feats=1, use_bond=None, expand_edge=True, update_edge=False, use_layer_norm=True):
     """Ordered ``{name: shape}`` for one model.
 
     kind: "lj" (SimpleMDNetNew), "water" (WaterMDNetNew), "dynbox" (WaterMDDynamicBoxNet).
+    update_edge: every layer owns an ``edge_layer_norm`` registered before ``edge_affine`` (nn_module.py:89-90).
+    use_layer_norm=False: ``norm_layers`` are ``BatchNorm1d`` with running statistics (nn_module.py:195-196).
     """
     D, H, De = encoding_size, hidden_dim, edge_embedding_dim
     if use_bond is None:
@@ -31,6 +33,9 @@ def param_shapes(kind="lj", encoding_size=128, hidden_dim=128, edge_embedding_di
         s["node_emb"] = (1, D)
     for l in range(conv_layer):
         p = f"graph_conv.conv.{l}."
+        if update_edge:
+            s[p + "edge_layer_norm.weight"] = (De,)
+            s[p + "edge_layer_norm.bias"] = (De,)
         # edge_affine = MLP(De, H, hidden_layer=2): Linear(De,128) act Linear(128,H); the inner
         # width is MLP's default hidden_dim=128, not the model's hidden_dim (nn_module.py:95)
         s[p + "edge_affine.mlp_layer.0.weight"] = (128, De)
@@ -57,6 +62,10 @@ def param_shapes(kind="lj", encoding_size=128, hidden_dim=128, edge_embedding_di
     for l in range(conv_layer):
         s[f"graph_conv.norm_layers.{l}.weight"] = (D,)
         s[f"graph_conv.norm_layers.{l}.bias"] = (D,)
+        if not use_layer_norm:
+            s[f"graph_conv.norm_layers.{l}.running_mean"] = (D,)
+            s[f"graph_conv.norm_layers.{l}.running_var"] = (D,)
+            s[f"graph_conv.norm_layers.{l}.num_batches_tracked"] = ()
     if expand_edge:
         s["edge_expand.centers"] = (N_RBF,)
     if kind != "lj":
@@ -83,8 +92,8 @@ def random_state_dict(seed=0, length_mean=0.0, length_std=1.0, as_torch=True, **
     """Random-init weights with torch-like scales, drawn from a numpy PCG64 stream.
 
     Linear weight/bias ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (torch's default bound),
-    LayerNorm weight ~ 1 + 0.1 N(0,1), LayerNorm bias ~ 0.1 N(0,1) (so that the affine
-    part is exercised), node_emb ~ N(0,1), RBF centres = linspace(0,1,40) as in
+    LayerNorm / BatchNorm weight ~ 1 + 0.1 N(0,1), bias ~ 0.1 N(0,1) (so that the affine
+    part is exercised), BatchNorm running_mean ~ 0.1 N(0,1), running_var ~ U(0.5, 1.5), node_emb ~ N(0,1), RBF centres = linspace(0,1,40) as in
     ``RBFExpansion`` (nn_module.py:237-239).
     """
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -99,6 +108,12 @@ def random_state_dict(seed=0, length_mean=0.0, length_std=1.0, as_torch=True, **
             v = np.linspace(0.0, 1.0, N_RBF).astype(np.float32)
         elif name == "node_emb":
             v = rng.standard_normal(shape).astype(np.float32)
+        elif name.endswith("running_mean"):
+            v = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        elif name.endswith("running_var"):
+            v = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        elif name.endswith("num_batches_tracked"):
+            v = np.zeros(shape, np.int64)
         elif "norm" in name and name.endswith("weight"):
             v = (1.0 + 0.1 * rng.standard_normal(shape)).astype(np.float32)
         elif "norm" in name and name.endswith("bias"):

@@ -68,12 +68,24 @@ def edge_encode(sd, feat):
     return _ln(sd, "edge_layer_norm", x)
 
 
-def mp_layer(sd, l, h, e, center, neigh, return_parts=False):
-    """One ``h <- conv_l(g, LN_l(h)) + h`` (nn_module.py:202 with :108-148).
+def _node_norm(sd, l, h):
+    """``norm_layers[l]``: LayerNorm, or eval-mode BatchNorm1d with its running statistics when the state dict
+    carries them (``use_layer_norm=False``, nn_module.py:193-196)."""
+    name = f"graph_conv.norm_layers.{l}"
+    if name + ".running_mean" in sd:
+        return Fnn.batch_norm(h, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"],
+                              sd[name + ".bias"], False, 0.0, 1e-5)
+    return _ln(sd, name, h)
 
-    Message flows neigh -> center: graph is ``dgl.graph((neigh, center))`` (:643)."""
+
+def mp_layer(sd, l, h, e, center, neigh, return_parts=False):
+    """One ``h <- conv_l(g, norm_l(h)) + h`` (nn_module.py:202 with :108-148).
+
+    Message flows neigh -> center: graph is ``dgl.graph((neigh, center))`` (:643).  With ``update_edge_emb`` the
+    layer also replaces the edge embedding by ``edge_layer_norm(e_emb)`` for the layers after it (:139-146); the new
+    embedding is returned in ``parts["e_next"]``."""
     p = f"graph_conv.conv.{l}."
-    hn = _ln(sd, f"graph_conv.norm_layers.{l}", h)
+    hn = _node_norm(sd, l, h)
     edge_code = _lin(sd, p + "edge_affine.mlp_layer.2", Fnn.silu(_lin(sd, p + "edge_affine.mlp_layer.0", e)))
     src_code = _lin(sd, p + "src_affine", hn)[neigh]
     dst_code = _lin(sd, p + "dst_affine", hn)[center]
@@ -83,7 +95,8 @@ def mp_layer(sd, l, h, e, center, neigh, return_parts=False):
     agg.index_add_(0, center, hn[neigh] * m)
     out = _lin(sd, p + "phi.mlp_layer.1", Fnn.silu(_lin(sd, p + "phi_dst", hn) + _lin(sd, p + "phi_edge", agg))) + h
     if return_parts:
-        return out, dict(hn=hn, m=m, agg=agg)
+        e_next = _ln(sd, p + "edge_layer_norm", m) if p + "edge_layer_norm.weight" in sd else e
+        return out, dict(hn=hn, m=m, agg=agg, e_next=e_next)
     return out
 
 
@@ -138,6 +151,7 @@ def forward(sd, kind, pos_lst, edge_lst, box, x=None, bond=None, return_intermed
     inter = dict(e=e, h=[h], agg=[], hn=[])
     for l in range(n_conv_layers(sd)):
         h, parts = mp_layer(sd, l, h, e, center, neigh, return_parts=True)
+        e = parts["e_next"]
         inter["h"].append(h)
         inter["agg"].append(parts["agg"])
         inter["hn"].append(parts["hn"])
@@ -168,5 +182,6 @@ def forward_dynbox(sd, pos_lst, x, box_lst, cutoff, bond=None):
     e, center, neigh = torch.cat(es), torch.cat(cs), torch.cat(ns)
     h = _lin(sd, "node_encoder", torch.as_tensor(x, dtype=torch.float32))
     for l in range(n_conv_layers(sd)):
-        h = mp_layer(sd, l, h, e, center, neigh)
+        h, parts = mp_layer(sd, l, h, e, center, neigh, return_parts=True)
+        e = parts["e_next"]
     return decode(sd, h)

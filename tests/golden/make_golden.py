@@ -123,6 +123,55 @@ def dynbox_case(name, seed):
     print(name, out.shape, "E", e_mine.shape[1], "sum", out.sum())
 
 
+def dynbox_variant_case(name, seed, n_atoms, D, H, De, layers, update_edge=False, expand_edge=True):
+    """WaterMDDynamicBoxNet beyond the 128-wide LayerNorm / RBF configuration: the 256 / 128 / 256 x 5 model of
+    code/water/test_script/test_nosehoover_hb.py:69-81, wider ones, ``update_edge`` (every layer re-normalises the edge
+    embedding, nn_module.py:139-146) and ``expand_edge=False`` (4 edge inputs, nn_module.py:312-313)."""
+    model = ref_nn.WaterMDDynamicBoxNet(1, D, 3, hidden_dim=H, conv_layer=layers, edge_embedding_dim=De,
+                                        drop_edge=False, use_layer_norm=True, update_edge=update_edge,
+                                        expand_edge=expand_edge)
+    kw = dict(kind="dynbox", use_bond=False, encoding_size=D, hidden_dim=H, edge_embedding_dim=De, conv_layer=layers,
+              update_edge=update_edge, expand_edge=expand_edge)
+    check_keys(model, **kw)
+    sd = random_state_dict(seed, 2.9, 0.9, **kw)
+    model.load_state_dict(sd)
+    model.eval()
+    pos = np.load(os.path.join(FIX, "water_init_pos.npy"))[:n_atoms].astype(np.float32)
+    box = np.array([12.4, 12.9, 13.3], dtype=np.float32)
+    x = torch.zeros(n_atoms, 1)
+    x[::3] = 1.0
+    with torch.no_grad():
+        out = model([torch.from_numpy(pos)], x, [box], 4.2).numpy()
+    mine = omodel.forward_dynbox(sd, [pos], x, [box], 4.2).numpy()
+    assert np.array_equal(out, mine), np.abs(out - mine).max()
+    e_mine, _, _ = onb.get_neighbor(pos, 4.2, box)
+    np.savez(os.path.join(HERE, name + ".npz"), force=out, seed=seed, box=box, pos=pos, n_edges=e_mine.shape[1],
+             dims=np.array([D, H, De, layers, int(update_edge), int(expand_edge)]))
+    print(name, out.shape, "E", e_mine.shape[1], "sum", out.sum())
+
+
+def lj_batchnorm_case(name, seed):
+    """SimpleMDNetNew with ``use_layer_norm=False``: eval-mode BatchNorm1d on the node features
+    (nn_module.py:193-196, :200-204) with non-trivial running statistics."""
+    box, rc = 27.27, 7.5
+    model = ref_nn.SimpleMDNetNew(128, 3, box, hidden_dim=128, conv_layer=4, edge_embedding_dim=128,
+                                  drop_edge=False, use_layer_norm=False)
+    check_keys(model, kind="lj", use_layer_norm=False)
+    sd = random_state_dict(seed, 5.2, 1.5, kind="lj", use_layer_norm=False)
+    model.load_state_dict(sd)
+    model.eval()
+    pos = np.load(os.path.join(FIX, "lj_init_pos.npy")).astype(np.float64)
+    edge = torch.from_numpy(onb.edges_jaxmd(pos, box, rc))
+    p = torch.from_numpy(np.mod(pos, box)).float()
+    with torch.no_grad():
+        out = model([p], [edge]).numpy()
+    mine = omodel.forward(sd, "lj", [p], [edge], box).numpy()
+    assert np.array_equal(out, mine), np.abs(out - mine).max()
+    np.savez(os.path.join(HERE, name + ".npz"), force=out, seed=seed, length_mean=5.2, length_std=1.5,
+             n_edges=np.array([edge.shape[1]]), pos=p.numpy()[None])
+    print(name, out.shape, "E", edge.shape[1], "sum", out.sum())
+
+
 def get_neighbor_case(name):
     """reference md_module.get_neighbor on both fixtures (scalar box)."""
     res = {}
@@ -148,3 +197,9 @@ if __name__ == "__main__":
     water_case("tip3p774_trainedstats", seed=4, length_mean=2.9, length_std=0.9)
     dynbox_case("dynbox192", seed=5)
     get_neighbor_case("get_neighbor")
+    dynbox_variant_case("dynbox192_w256", seed=6, n_atoms=192, D=256, H=128, De=256, layers=5)
+    dynbox_variant_case("dynbox192_update_edge", seed=7, n_atoms=192, D=128, H=128, De=128, layers=3, update_edge=True,
+                        expand_edge=False)
+    dynbox_variant_case("dynbox96_w512", seed=8, n_atoms=96, D=512, H=256, De=384, layers=2)
+    dynbox_variant_case("dynbox96_w768", seed=9, n_atoms=96, D=768, H=512, De=768, layers=2, update_edge=True)
+    lj_batchnorm_case("lj258_batchnorm", seed=10)

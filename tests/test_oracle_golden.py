@@ -52,6 +52,31 @@ def test_dynbox_forward_matches_reference(golden_dir):
     assert np.abs(out - g["force"]).max() <= TOL
 
 
+@pytest.mark.parametrize("name", ["dynbox192_w256", "dynbox192_update_edge", "dynbox96_w512", "dynbox96_w768"])
+def test_dynbox_variants_match_reference(golden_dir, name):
+    """wide (256 / 512 / 768), ``update_edge`` and ``expand_edge=False`` configurations of WaterMDDynamicBoxNet"""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    D, H, De, L, upd, exp = [int(v) for v in g["dims"]]
+    sd = random_state_dict(int(g["seed"]), 2.9, 0.9, kind="dynbox", use_bond=False, encoding_size=D, hidden_dim=H,
+                           edge_embedding_dim=De, conv_layer=L, update_edge=bool(upd), expand_edge=bool(exp))
+    n = g["pos"].shape[0]
+    x = torch.zeros(n, 1)
+    x[::3] = 1.0
+    out = omodel.forward_dynbox(sd, [g["pos"]], x, [g["box"]], 4.2).numpy()
+    assert np.abs(out - g["force"]).max() <= TOL
+
+
+def test_lj_batchnorm_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "lj258_batchnorm.npz"))
+    sd = random_state_dict(int(g["seed"]), float(g["length_mean"]), float(g["length_std"]), kind="lj",
+                           use_layer_norm=False)
+    p = torch.from_numpy(g["pos"][0])
+    edge = torch.from_numpy(onb.edges_bruteforce(g["pos"][0], 27.27, 7.5))
+    assert edge.shape[1] == int(g["n_edges"][0])
+    out = omodel.forward(sd, "lj", [p], [edge], 27.27).numpy()
+    assert np.abs(out - g["force"]).max() <= TOL
+
+
 def test_get_neighbor_matches_reference(golden_dir, fixtures_dir):
     g = np.load(os.path.join(golden_dir, "get_neighbor.npz"))
     for tag, fn, box, rc in (("lj", "lj_init_pos.npy", 27.27, 7.5), ("water", "water_init_pos.npy", 20.0, 4.2)):
