@@ -30,7 +30,7 @@ class GamdError(RuntimeError):
 class ModelDesc(ctypes.Structure):
     _fields_ = [("kind", c_int32), ("encoding_size", c_int32), ("hidden_dim", c_int32), ("edge_dim", c_int32),
                 ("conv_layer", c_int32), ("in_feats", c_int32), ("use_bond", c_int32), ("expand_edge", c_int32),
-                ("precision", c_int32)]
+                ("precision", c_int32), ("update_edge", c_int32), ("batch_norm", c_int32)]
 
 
 NHC_MAX = 16
@@ -162,10 +162,11 @@ class Context:
     """One model instance on one device (wraps ``gamd_ctx*``)."""
 
     def __init__(self, kind=MODEL_LJ, encoding_size=128, hidden_dim=128, edge_dim=128, conv_layer=4,
-                 in_feats=0, use_bond=False, expand_edge=True, precision=PREC_FP32, device=0):
+                 in_feats=0, use_bond=False, expand_edge=True, precision=PREC_FP32, device=0, update_edge=False,
+                 batch_norm=False):
         self.lib = load_library()
         self.desc = ModelDesc(kind, encoding_size, hidden_dim, edge_dim, conv_layer, in_feats, int(use_bond),
-                              int(expand_edge), precision)
+                              int(expand_edge), precision, int(update_edge), int(batch_norm))
         self._h = c_void_p()
         rc = self.lib.gamd_create(device, ctypes.byref(self.desc), ctypes.byref(self._h))
         if rc:
@@ -199,6 +200,7 @@ class Context:
     def load_state_dict(self, sd):
         for k, v in sd.items():
             a = np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
+            a = a.reshape(-1) if a.ndim == 0 else a       # BatchNorm's num_batches_tracked is a 0-d tensor
             self._check(self.lib.gamd_load_weight(self._h, k.encode(), a.ctypes.data, a.size))
 
     def set_scaler(self, mean, var):

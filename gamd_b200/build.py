@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libgamd_b200.so")
-SOURCES = ["capi.cu", "neighbor.cu", "model_fp32.cu", "mp_tc.cu", "mp_tc3.cu", "mp_tc2cta.cu", "enc_tc.cu", "node_tc.cu", "integrate.cu", "thermostat.cu"]
+SOURCES = ["capi.cu", "neighbor.cu", "model_fp32.cu", "model_wide.cu", "mp_tc.cu", "mp_tc3.cu", "mp_tc2cta.cu", "enc_tc.cu", "node_tc.cu", "integrate.cu", "thermostat.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -27,6 +27,10 @@ std::vector<WSpec> expected_weights(const gamd_model_desc& d) {
       v.push_back({p + n + ".weight", out, in});
       v.push_back({p + n + ".bias", out, 0});
     };
+    if (d.update_edge) {
+      v.push_back({p + "edge_layer_norm.weight", De, 0});
+      v.push_back({p + "edge_layer_norm.bias", De, 0});
+    }
     lin("edge_affine.mlp_layer.0", 128, De);
     lin("edge_affine.mlp_layer.2", H, 128);
     lin("src_affine", H, D);
@@ -40,6 +44,11 @@ std::vector<WSpec> expected_weights(const gamd_model_desc& d) {
   for (int l = 0; l < d.conv_layer; l++) {
     v.push_back({"graph_conv.norm_layers." + std::to_string(l) + ".weight", D, 0});
     v.push_back({"graph_conv.norm_layers." + std::to_string(l) + ".bias", D, 0});
+    if (d.batch_norm) {
+      v.push_back({"graph_conv.norm_layers." + std::to_string(l) + ".running_mean", D, 0});
+      v.push_back({"graph_conv.norm_layers." + std::to_string(l) + ".running_var", D, 0});
+      v.push_back({"graph_conv.norm_layers." + std::to_string(l) + ".num_batches_tracked", 1, 0});
+    }
   }
   if (d.expand_edge) v.push_back({"edge_expand.centers", GAMD_NRBF, 0});
   if (d.kind != GAMD_MODEL_LJ) {
@@ -75,6 +84,7 @@ struct Carver {
 };
 
 void carve(gamd_ctx* ctx, Carver& c, int64_t A, int64_t E) {
+  const size_t D = ctx->desc.encoding_size, H = ctx->desc.hidden_dim, De = ctx->desc.edge_dim;
   const int64_t rs_blocks = (A + 2047) / 2048 + 1;
   ctx->cap_cells = 8 * A + 1024;
   for (int i = 0; i < 2; i++) {
@@ -99,14 +109,15 @@ void carve(gamd_ctx* ctx, Carver& c, int64_t A, int64_t E) {
   ctx->d_stepctr = c.take<int>(4);
   ctx->col_idx = c.take<int>(E);
   ctx->edge_dst = c.take<int>(E);
-  ctx->e_emb = c.take<float>((size_t)(E + 256) * GAMD_NF);   // fp32 rows, or 64 KB bf16 hi/lo blobs per 128-edge tile
-  ctx->h = c.take<float>((size_t)A * GAMD_NF);
-  ctx->hn = c.take<float>((size_t)A * GAMD_NF);
-  ctx->srcA = c.take<float>((size_t)A * GAMD_NF);
-  ctx->dstA = c.take<float>((size_t)A * GAMD_NF);
-  ctx->pd = c.take<float>((size_t)A * GAMD_NF);
-  ctx->agg = c.take<float>((size_t)A * GAMD_NF);
-  ctx->part = c.take<float>((size_t)(E / 32 + 4) * 2 * GAMD_NF);
+  ctx->e_emb = c.take<float>((size_t)(E + 256) * De);   // fp32 rows, or 64 KB bf16 hi/lo blobs per 128-edge tile
+  ctx->h = c.take<float>((size_t)A * D);
+  ctx->hn = c.take<float>((size_t)A * D);
+  ctx->srcA = c.take<float>((size_t)A * H);
+  ctx->dstA = c.take<float>((size_t)A * H);
+  ctx->pd = c.take<float>((size_t)A * H);
+  ctx->agg = c.take<float>((size_t)A * D);
+  // partial sums of receiver runs cut by an edge tile: 32-edge blocks (tensor path), or the generic path's 16 r-row tiles
+  ctx->part = c.take<float>(ctx->wide ? (size_t)(E / (16 * ctx->wide_r) + 4) * 2 * D : (size_t)(E / 32 + 4) * 2 * GAMD_NF);
   ctx->tile_list[0] = c.take<int>(E / 128 + 4);
   ctx->tile_list[1] = c.take<int>(E / 128 + 4);
   ctx->tile_count = c.take<int>(4);
@@ -261,9 +272,23 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
                    (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
     return GAMD_ENOGPU;
   }
-  if (desc->encoding_size != GAMD_NF || desc->hidden_dim != GAMD_NF || desc->edge_dim != GAMD_NF) {
-    g_create_err = "only encoding_size = hidden_dim = edge_embedding_dim = 128 is built";
-    return GAMD_EUNSUPPORTED;
+  const bool wide = desc->encoding_size != GAMD_NF || desc->hidden_dim != GAMD_NF || desc->edge_dim != GAMD_NF ||
+                    desc->update_edge || desc->batch_norm || !desc->expand_edge;
+  int wide_r = 4, wide_xs = GAMD_NF + 4;
+  if (wide) {
+    for (int v : {desc->encoding_size, desc->hidden_dim, desc->edge_dim})
+      if (v < 128 || v > 1024 || v % 128) {
+        g_create_err = "encoding_size, hidden_dim and edge_embedding_dim must be multiples of 128 in 128..1024";
+        return GAMD_EUNSUPPORTED;
+      }
+    if (desc->update_edge && desc->edge_dim != desc->encoding_size) {
+      g_create_err = "update_edge needs edge_embedding_dim == encoding_size (edge_layer_norm acts on e_emb)";
+      return GAMD_EINVAL;
+    }
+    if (wide_plan(desc->encoding_size, desc->hidden_dim, desc->edge_dim, &wide_r, &wide_xs)) {
+      g_create_err = "model too wide for the shared-memory tiles";
+      return GAMD_EUNSUPPORTED;
+    }
   }
   if (desc->conv_layer < 1 || desc->conv_layer > 8) {
     g_create_err = "conv_layer must be in 1..8";
@@ -284,6 +309,10 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   gamd_ctx* ctx = new gamd_ctx();
   ctx->device = device;
   ctx->desc = *desc;
+  ctx->wide = wide;
+  ctx->wide_r = wide_r;
+  ctx->wide_xs = wide_xs;
+  if (wide) ctx->desc.precision = GAMD_PREC_FP32;   // the generic-width path computes in fp32 whatever was asked for
   ctx->use_graphs = getenv("GAMD_NO_GRAPH") == nullptr;
   ctx->dbg_timeline = getenv("GAMD_TIMELINE") != nullptr;
   if (const char* e = getenv("GAMD_WAIT_HINT_NS")) ctx->wait_hint_ns = atoi(e);
@@ -462,41 +491,50 @@ int gamd_finalize_weights(gamd_ctx* ctx) {
   };
   ModelW& mw = ctx->mw;
   mw = ModelW{};
-  const int NFv = GAMD_NF;
+  const int D = d.encoding_size, H = d.hidden_dim, De = d.edge_dim;
   for (int l = 0; l < d.conv_layer; l++) {
     std::string p = "graph_conv.conv." + std::to_string(l) + ".";
+    std::string nl = "graph_conv.norm_layers." + std::to_string(l) + ".";
     LayerW& L = mw.layer[l];
-    push(&L.ea0_t, transposed(p + "edge_affine.mlp_layer.0.weight", NFv, NFv, NFv));
+    push(&L.ea0_t, transposed(p + "edge_affine.mlp_layer.0.weight", 128, De, De));
     push(&L.ea0_b, ctx->host_w[p + "edge_affine.mlp_layer.0.bias"]);
-    push(&L.ea2_t, transposed(p + "edge_affine.mlp_layer.2.weight", NFv, NFv, NFv));
+    push(&L.ea2_t, transposed(p + "edge_affine.mlp_layer.2.weight", H, 128, 128));
     push(&L.ea2_b, ctx->host_w[p + "edge_affine.mlp_layer.2.bias"]);
-    push(&L.src_t, transposed(p + "src_affine.weight", NFv, NFv, NFv));
+    push(&L.src_t, transposed(p + "src_affine.weight", H, D, D));
     push(&L.src_b, ctx->host_w[p + "src_affine.bias"]);
-    push(&L.dst_t, transposed(p + "dst_affine.weight", NFv, NFv, NFv));
+    push(&L.dst_t, transposed(p + "dst_affine.weight", H, D, D));
     push(&L.dst_b, ctx->host_w[p + "dst_affine.bias"]);
-    push(&L.te1_t, transposed(p + "theta_edge.mlp_layer.1.weight", NFv, NFv, NFv));
+    push(&L.te1_t, transposed(p + "theta_edge.mlp_layer.1.weight", H, H, H));
     push(&L.te1_b, ctx->host_w[p + "theta_edge.mlp_layer.1.bias"]);
-    push(&L.te3_t, transposed(p + "theta_edge.mlp_layer.3.weight", NFv, NFv, NFv));
+    push(&L.te3_t, transposed(p + "theta_edge.mlp_layer.3.weight", D, H, H));
     push(&L.te3_b, ctx->host_w[p + "theta_edge.mlp_layer.3.bias"]);
-    push(&L.pdst_t, transposed(p + "phi_dst.weight", NFv, NFv, NFv));
+    push(&L.pdst_t, transposed(p + "phi_dst.weight", H, D, D));
     push(&L.pdst_b, ctx->host_w[p + "phi_dst.bias"]);
-    push(&L.pedge_t, transposed(p + "phi_edge.weight", NFv, NFv, NFv));
+    push(&L.pedge_t, transposed(p + "phi_edge.weight", H, D, D));
     push(&L.pedge_b, ctx->host_w[p + "phi_edge.bias"]);
-    push(&L.phi_t, transposed(p + "phi.mlp_layer.1.weight", NFv, NFv, NFv));
+    push(&L.phi_t, transposed(p + "phi.mlp_layer.1.weight", D, H, H));
     push(&L.phi_b, ctx->host_w[p + "phi.mlp_layer.1.bias"]);
-    push(&L.ln_w, ctx->host_w["graph_conv.norm_layers." + std::to_string(l) + ".weight"]);
-    push(&L.ln_b, ctx->host_w["graph_conv.norm_layers." + std::to_string(l) + ".bias"]);
+    push(&L.ln_w, ctx->host_w[nl + "weight"]);
+    push(&L.ln_b, ctx->host_w[nl + "bias"]);
+    if (d.batch_norm) {
+      push(&L.bn_mean, ctx->host_w[nl + "running_mean"]);
+      push(&L.bn_var, ctx->host_w[nl + "running_var"]);
+    }
+    if (d.update_edge) {
+      push(&L.uln_w, ctx->host_w[p + "edge_layer_norm.weight"]);
+      push(&L.uln_b, ctx->host_w[p + "edge_layer_norm.bias"]);
+    }
   }
   const int n_in = 4 + (d.expand_edge ? GAMD_NRBF : 0) + (d.use_bond ? 1 : 0);
-  push(&mw.enc0_t, transposed("edge_encoder.mlp_layer.0.weight", NFv, n_in, 64));
+  push(&mw.enc0_t, transposed("edge_encoder.mlp_layer.0.weight", H, n_in, d.expand_edge ? 64 : 32));
   push(&mw.enc0_b, ctx->host_w["edge_encoder.mlp_layer.0.bias"]);
-  push(&mw.enc2_t, transposed("edge_encoder.mlp_layer.2.weight", NFv, NFv, NFv));
+  push(&mw.enc2_t, transposed("edge_encoder.mlp_layer.2.weight", H, H, H));
   push(&mw.enc2_b, ctx->host_w["edge_encoder.mlp_layer.2.bias"]);
-  push(&mw.enc4_t, transposed("edge_encoder.mlp_layer.4.weight", NFv, NFv, NFv));
+  push(&mw.enc4_t, transposed("edge_encoder.mlp_layer.4.weight", De, H, H));
   push(&mw.enc4_b, ctx->host_w["edge_encoder.mlp_layer.4.bias"]);
   push(&mw.eln_w, ctx->host_w["edge_layer_norm.weight"]);
   push(&mw.eln_b, ctx->host_w["edge_layer_norm.bias"]);
-  push(&mw.dec0_t, transposed("graph_decoder.mlp_layer.0.weight", NFv, NFv, NFv));
+  push(&mw.dec0_t, transposed("graph_decoder.mlp_layer.0.weight", H, D, D));
   push(&mw.dec0_b, ctx->host_w["graph_decoder.mlp_layer.0.bias"]);
   push(&mw.dec2_w, ctx->host_w["graph_decoder.mlp_layer.2.weight"]);
   push(&mw.dec2_b, ctx->host_w["graph_decoder.mlp_layer.2.bias"]);
@@ -1141,6 +1179,10 @@ int gamd_dd_begin(gamd_ctx* ctx, const double* d_pos, int64_t n_own, int64_t n_l
     ctx->err = "this model needs the node feature vector";
     return GAMD_EINVAL;
   }
+  if (ctx->wide) {
+    ctx->err = "domain decomposition is built for the 128-wide tensor-core models only";
+    return GAMD_EUNSUPPORTED;
+  }
   if (ctx->desc.use_bond) {
     // the bond flag is looked up by frame-local atom id; a rank's local numbering is not the global one
     ctx->err = "domain decomposition of a model with the bond flag is not built (bond look-up needs global atom ids)";
@@ -1350,12 +1392,12 @@ int gamd_debug_ptr(gamd_ctx* ctx, const char* name, void** d_ptr, int64_t* n_byt
   else if (n == "n_edges") p = ctx->n_edges, nb = 4;
   else if (n == "pos_sorted") p = ctx->pos_feat_s, nb = 16 * A;
   else if (n == "pos_nbr_sorted") p = ctx->pos_nbr_s, nb = 16 * A;
-  else if (n == "e_emb") p = ctx->e_emb, nb = 4 * E * GAMD_NF;
-  else if (n == "h") p = ctx->h, nb = 4 * A * GAMD_NF;
-  else if (n == "hn") p = ctx->hn, nb = 4 * A * GAMD_NF;
-  else if (n == "agg") p = ctx->agg, nb = 4 * A * GAMD_NF;
+  else if (n == "e_emb") p = ctx->e_emb, nb = 4 * E * ctx->desc.edge_dim;
+  else if (n == "h") p = ctx->h, nb = 4 * A * ctx->desc.encoding_size;
+  else if (n == "hn") p = ctx->hn, nb = 4 * A * ctx->desc.encoding_size;
+  else if (n == "agg") p = ctx->agg, nb = 4 * A * ctx->desc.encoding_size;
   else if (n == "pred") p = ctx->pred, nb = 4 * A * 3;
-  else if (n == "dbg") p = ctx->e_emb + (size_t)E * GAMD_NF, nb = 256 * GAMD_NF * 4;
+  else if (n == "dbg") p = ctx->e_emb + (size_t)E * ctx->desc.edge_dim, nb = 256 * GAMD_NF * 4;
   else {
     ctx->err = "unknown debug buffer: " + n;
     return GAMD_EINVAL;

@@ -7,7 +7,7 @@
 #include <vector>
 #include "../../include/gamd_b200.h"
 
-#define GAMD_NF 128          // feature width the kernels are built for (D = H = De = 128)
+#define GAMD_NF 128          // feature width the tensor-core / 128-wide fp32 kernels are built for (D = H = De = 128)
 #define GAMD_EDGE_TILE 64    // edges per tile of the fp32 edge kernels
 #define GAMD_NODE_TILE 64    // nodes per tile of the node kernels
 #define GAMD_MAX_BOND 4      // bonded partners kept per atom (water: O has 2, H has 1)
@@ -30,7 +30,9 @@ struct LayerW {
   const float *te1_t, *te1_b, *te3_t, *te3_b;
   const float *pdst_t, *pdst_b, *pedge_t, *pedge_b;
   const float *phi_t, *phi_b;
-  const float *ln_w, *ln_b;
+  const float *ln_w, *ln_b;           // norm_layers[l]: LayerNorm, or BatchNorm1d when bn_mean != nullptr
+  const float *bn_mean, *bn_var;      // BatchNorm1d running statistics (use_layer_norm = False), else nullptr
+  const float *uln_w, *uln_b;         // conv[l].edge_layer_norm (update_edge), else nullptr
 };
 
 struct ModelW {
@@ -133,6 +135,9 @@ struct gamd_ctx {
   int mp_variant = 0;
   int enc_variant = 3;         // edge encoder: 3 = three tiles in flight (in-place TMEM operands), 0 = two tiles
   int64_t model_atoms = 0;     // atoms of the forward pass in flight (model_begin)
+  // generic-width fp32 path (model_wide.cu): widths other than 128, update_edge, no RBF expansion, BatchNorm
+  bool wide = false;
+  int wide_r = 4, wide_xs = 132;   // rows per thread (tile = 16 r rows) and shared-memory row stride
   int mp_small_atoms = 4096;   // systems up to this size use the two-tile single-CTA edge kernel (GAMD_MP_SMALL_ATOMS)
 
   // halo exchange over peer memory: buffers this rank exposes (cudaMalloc + IPC handle) / neighbours' buffers it opened
@@ -178,7 +183,7 @@ void prof_mark(gamd_ctx* ctx, const char* stage, cudaStream_t st);   // call bef
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16, GAMD_ATTR_MP_TC2 = 32, GAMD_ATTR_NBR_SMALL = 64, GAMD_ATTR_ENC_TC3 = 128 };
+enum { GAMD_ATTR_FP32 = 1, GAMD_ATTR_MP_TC = 2, GAMD_ATTR_ENC_TC = 4, GAMD_ATTR_NODE_TC = 8, GAMD_ATTR_MP_TC3 = 16, GAMD_ATTR_MP_TC2 = 32, GAMD_ATTR_NBR_SMALL = 64, GAMD_ATTR_ENC_TC3 = 128, GAMD_ATTR_WIDE = 256 };
 
 // every stream entry point runs on the context's device, whatever device the calling thread had current
 #define GAMD_ENTER(ctx)                                                                  \
@@ -214,6 +219,13 @@ int model_layer_edges(gamd_ctx* ctx, int l, cudaStream_t st, int which);
 int model_layer_nodes(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 int model_forward(gamd_ctx* ctx, const float4* pos_feat, const float* feat, const int* orig_id,
                        int64_t n_atoms, int atoms_per_frame, const float box[3], cudaStream_t st);
+
+// generic-width fp32 path (model_wide.cu)
+int wide_plan(int D, int H, int De, int* r_out, int* xs_out);
+int wide_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64_t n_atoms, int atoms_per_frame,
+               const float box[3], cudaStream_t st);
+int wide_layer_edges(gamd_ctx* ctx, int l, cudaStream_t st);
+int wide_layer_nodes(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st);
 
 int integ_first_half(gamd_ctx* ctx, double* x, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);
 int integ_second_half(gamd_ctx* ctx, double* v, const double* f, const double* mass, int64_t n, double dt, cudaStream_t st);

@@ -552,6 +552,7 @@ static NodeArgs node_args(const ModelW& mw) {
 // edge encoder + layer-0 node prologue (h0, LN_0, src/dst/phi_dst affines) for n_atoms rows
 int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64_t n_atoms, int atoms_per_frame,
                 const float box[3], cudaStream_t st) {
+  if (ctx->wide) return wide_begin(ctx, pos_feat, orig_id, n_atoms, atoms_per_frame, box, st);
   int rc = model_attrs(ctx);
   if (rc) return rc;
   ctx->model_atoms = n_atoms;
@@ -594,6 +595,7 @@ int model_begin(gamd_ctx* ctx, const float4* pos_feat, const int* orig_id, int64
 int model_layer_edges(gamd_ctx* ctx, int l, cudaStream_t st, int which) {
   const ModelW& mw = ctx->mw;
   const bool tcpath = ctx->desc.precision != GAMD_PREC_FP32;
+  if (ctx->wide && which < 0) return wide_layer_edges(ctx, l, st);
   if (!tcpath && which >= 0) {
     ctx->err = "tile-split layers need a tensor-core precision (bf16x3 / bf16)";
     return GAMD_EUNSUPPORTED;
@@ -614,6 +616,7 @@ int model_layer_edges(gamd_ctx* ctx, int l, cudaStream_t st, int which) {
 
 // message-passing layer l, node part: next layer's LN + affines, or the force decoder after the last layer
 int model_layer_nodes(gamd_ctx* ctx, int l, const float4* pos_feat, int64_t n_atoms, cudaStream_t st) {
+  if (ctx->wide) return wide_layer_nodes(ctx, l, pos_feat, n_atoms, st);
   const ModelW& mw = ctx->mw;
   const int node_tiles = ceil_div(n_atoms, TM);
   const int grid_node = node_tiles < ctx->sm_count * 3 ? node_tiles : ctx->sm_count * 3;

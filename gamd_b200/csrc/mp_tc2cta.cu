@@ -160,15 +160,44 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(hx, t, hx);
 }
 
+// 2^t for two elements on the FMA / ALU pipes instead of MUFU.EX2 (the SiLU stages keep the 16-lane XU pipe 75-80 % busy
+// while three tiles run their epilogues side by side): t clamped to [-126, 126], n = rint(t) by the magic-number add,
+// 2^f on [-0.5, 0.5] as the degree-6 Taylor polynomial (relative error < 1.6e-7, ex2.approx: 2 ulp), the exponent
+// spliced in with an integer shift-add.
+__device__ __forceinline__ void ex2_poly_pair(float t0, float t1, float& e0, float& e1) {
+  t0 = fminf(fmaxf(t0, -126.f), 126.f);
+  t1 = fminf(fmaxf(t1, -126.f), 126.f);
+  const f32x2 T = pk2(t0, t1);
+  const f32x2 TM = add2(T, pk2(12582912.f, 12582912.f));                 // 1.5 * 2^23 + n
+  const f32x2 N = add2(TM, pk2(-12582912.f, -12582912.f));
+  const f32x2 F = fma2(N, pk2(-1.f, -1.f), T);
+  f32x2 P = fma2(pk2(1.5403530393381606e-4f, 1.5403530393381606e-4f), F, pk2(1.3333558146428443e-3f, 1.3333558146428443e-3f));
+  P = fma2(P, F, pk2(9.618129107628477e-3f, 9.618129107628477e-3f));
+  P = fma2(P, F, pk2(5.550410866482158e-2f, 5.550410866482158e-2f));
+  P = fma2(P, F, pk2(2.402265069591007e-1f, 2.402265069591007e-1f));
+  P = fma2(P, F, pk2(6.931471805599453e-1f, 6.931471805599453e-1f));
+  P = fma2(P, F, pk2(1.f, 1.f));
+  float p0, p1, m0, m1;
+  unpk2(P, p0, p1);
+  unpk2(TM, m0, m1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(m0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(m1) << 23));
+}
+
 // x -> silu(x) for two elements, split into bf16 hi / lo pairs; packed fp32x2 arithmetic halves the FMA-pipe
-// instruction count of the (issue-bound) activation stages
+// instruction count of the (issue-bound) activation stages.  POLY: the exponential on the FMA pipe (ex2_poly_pair)
+template <bool POLY = false>
 __device__ __forceinline__ void silu_split_pair(f32x2 X, uint32_t& hi, uint32_t& lo) {
   const f32x2 T = mul2(X, pk2(-1.4426950408889634f, -1.4426950408889634f));
   float t0, t1;
   unpk2(T, t0, t1);
   float e0, e1;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  if (POLY) {
+    ex2_poly_pair(t0, t1, e0, e1);
+  } else {
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  }
   const f32x2 U = add2(pk2(e0, e1), pk2(1.f, 1.f));
   float u0, u1;
   unpk2(U, u0, u1);
@@ -186,7 +215,7 @@ __device__ __forceinline__ void silu_split_pair(f32x2 X, uint32_t& hi, uint32_t&
 }
 
 // epilogue of GEMM stage S for my 64 columns (4 chunks of 16)
-template <int S, bool EXACT, bool NSPLIT>
+template <int S, bool EXACT, bool NSPLIT, int POLY = 0>
 __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
   float4 dn[4];
   if (S == 1) {
@@ -238,8 +267,9 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
           X0 = add2(X0, add2(pk2(sv.x, sv.y), pk2(dc[j4].x, dc[j4].y)));
           X1 = add2(X1, add2(pk2(sv.z, sv.w), pk2(dc[j4].z, dc[j4].w)));
         }
-        silu_split_pair(X0, h[2 * j4], l[2 * j4]);
-        silu_split_pair(X1, h[2 * j4 + 1], l[2 * j4 + 1]);
+        // POLY = 1: every second pair's exponential leaves the XU pipe (MUFU work -25 %), 2: every pair's (-50 %)
+        silu_split_pair<POLY == 2>(X0, h[2 * j4], l[2 * j4]);
+        silu_split_pair<POLY != 0>(X1, h[2 * j4 + 1], l[2 * j4 + 1]);
       }
       tmem_st8(c.Dc + coff<NSPLIT>(cc), h);        // in place over the accumulator chunk just read: [hi pairs | lo pairs]
       tmem_st8(c.Dc + coff<NSPLIT>(cc) + 8, l);
@@ -358,7 +388,7 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
   }
 }
 
-template <bool SAFE_WAR, bool NSPLIT, bool SETUP1>
+template <bool SAFE_WAR, bool NSPLIT, bool SETUP1, int POLY = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edge_tc2(MpTcArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
   SmemTC& sm = *reinterpret_cast<SmemTC*>(raw);
@@ -588,7 +618,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
   c.Dc = tb + lane_base + sm.home[g] * 128u;       \
   c.d_par1 = d_par ^ 1u;                           \
   if (dbg_on) dbg_rec[dbg_n++] = gtime();        \
-  if (exact) stage_epilogue<S, true, NSPLIT>(c);   \
+  if (exact) stage_epilogue<S, true, NSPLIT, POLY>(c);   \
   else stage_epilogue<S, false, NSPLIT>(c);        \
   if (S < 3) {                                     \
     tmem_wait_st();                                \
@@ -753,6 +783,8 @@ int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, boo
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->attr_mask |= GAMD_ATTR_MP_TC2;
   }
   MpTcArgs a;
@@ -779,7 +811,9 @@ int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, boo
   int grid = which == 0 && reserve > 0 && reserve < ctx->sm_count ? ctx->sm_count - reserve : ctx->sm_count;
   grid &= ~1;       // whole CTA pairs
   // nsplit needs the N-split row order of the pair weight images (capi.cu builds them by ctx->mp_variant)
-  if (ctx->mp_variant == 8) k_mp_edge_tc2<false, false, true><<<grid, THREADS, smem, st>>>(a);
+  if (ctx->mp_variant == 9) k_mp_edge_tc2<false, false, true, 1><<<grid, THREADS, smem, st>>>(a);
+  else if (ctx->mp_variant == 10) k_mp_edge_tc2<false, false, true, 2><<<grid, THREADS, smem, st>>>(a);
+  else if (ctx->mp_variant == 8) k_mp_edge_tc2<false, false, true><<<grid, THREADS, smem, st>>>(a);
   else if (nsplit) k_mp_edge_tc2<false, true, false><<<grid, THREADS, smem, st>>>(a);
   else if (safe_war) k_mp_edge_tc2<true, false, false><<<grid, THREADS, smem, st>>>(a);
   else k_mp_edge_tc2<false, false, false><<<grid, THREADS, smem, st>>>(a);

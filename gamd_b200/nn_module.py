@@ -53,9 +53,10 @@ class SmoothConvLayerNew(nn.Module):
     def __init__(self, in_node_feats, in_edge_feats, out_node_feats, hidden_dim=128, activation="relu",
                  drop_edge=True, update_edge_emb=False):
         super().__init__()
-        if update_edge_emb:
-            raise NotImplementedError("update_edge_emb=True (dynamic-box variant) is not built yet")
         self.drop_edge = drop_edge
+        self.update_edge_emb = update_edge_emb
+        if update_edge_emb:     # registered first, as in the reference, so that the state-dict key order matches
+            self.edge_layer_norm = nn.LayerNorm(in_edge_feats)
         self.edge_affine = MLP(in_edge_feats, hidden_dim, activation=activation, hidden_layer=2)
         self.src_affine = nn.Linear(in_node_feats, hidden_dim)
         self.dst_affine = nn.Linear(in_node_feats, hidden_dim)
@@ -68,7 +69,7 @@ class SmoothConvLayerNew(nn.Module):
 
 
 class SmoothConvBlockNew(nn.Module):
-    """Stack of layers + per-layer LayerNorm (nn_module.py:151-196)."""
+    """Stack of layers + per-layer LayerNorm or (eval-mode) BatchNorm1d (nn_module.py:151-196)."""
 
     def __init__(self, in_node_feats, out_node_feats, hidden_dim=128, conv_layer=3, edge_emb_dim=64,
                  use_layer_norm=False, use_batch_norm=True, drop_edge=False, activation="relu",
@@ -76,13 +77,15 @@ class SmoothConvBlockNew(nn.Module):
         super().__init__()
         if use_batch_norm == use_layer_norm and use_batch_norm:
             raise Exception("Only one type of normalization at a time")
-        if not use_layer_norm:
-            raise NotImplementedError("only the LayerNorm variant (all shipped configs) is built")
+        if not (use_layer_norm or use_batch_norm):
+            raise NotImplementedError("the variant without any node normalisation is not built")
+        self.use_layer_norm, self.use_batch_norm = use_layer_norm, use_batch_norm
         self.conv = nn.ModuleList(
             SmoothConvLayerNew(in_node_feats if l == 0 else out_node_feats, edge_emb_dim, out_node_feats,
                                hidden_dim=hidden_dim, activation=activation, drop_edge=drop_edge,
                                update_edge_emb=update_egde_emb) for l in range(conv_layer))
-        self.norm_layers = nn.ModuleList(nn.LayerNorm(out_node_feats) for _ in range(conv_layer))
+        self.norm_layers = nn.ModuleList((nn.LayerNorm if use_layer_norm else nn.BatchNorm1d)(out_node_feats)
+                                         for _ in range(conv_layer))
 
 
 class RBFExpansion(nn.Module):
@@ -100,17 +103,19 @@ class _MDNetBase(nn.Module):
     _kind = _capi.MODEL_LJ
 
     def _init_common(self, encoding_size, out_feats, box_size, hidden_dim, conv_layer, edge_embedding_dim,
-                     drop_edge, use_layer_norm, n_edge_in):
+                     drop_edge, use_layer_norm, n_edge_in, update_edge=False, expand_edge=True):
         if out_feats != 3:
             raise NotImplementedError("out_feats must be 3 (forces)")
         self.graph_conv = SmoothConvBlockNew(in_node_feats=encoding_size, out_node_feats=encoding_size,
                                              hidden_dim=hidden_dim, conv_layer=conv_layer,
                                              edge_emb_dim=edge_embedding_dim, use_layer_norm=use_layer_norm,
                                              use_batch_norm=not use_layer_norm, drop_edge=drop_edge,
-                                             activation="silu")
+                                             activation="silu", update_egde_emb=update_edge)
         self.edge_emb_dim = edge_embedding_dim
-        self.edge_expand = RBFExpansion(high=1, gap=0.025)
-        assert len(self.edge_expand.centers) == N_RBF
+        self._update_edge, self._batch_norm, self._expand_edge = bool(update_edge), not use_layer_norm, bool(expand_edge)
+        if expand_edge:
+            self.edge_expand = RBFExpansion(high=1, gap=0.025)
+            assert len(self.edge_expand.centers) == N_RBF
         self.length_mean = nn.Parameter(torch.tensor([0.]), requires_grad=False)
         self.length_std = nn.Parameter(torch.tensor([1.]), requires_grad=False)
         self.box_size = torch.from_numpy(box_size).float() if isinstance(box_size, np.ndarray) else box_size
@@ -147,9 +152,10 @@ class _MDNetBase(nn.Module):
                                                     "(there is no CPU fallback)")
             self._ctx = _capi.Context(kind=self._kind, encoding_size=D, hidden_dim=H, edge_dim=De, conv_layer=L,
                                       in_feats=0 if self._kind == _capi.MODEL_LJ else 1,
-                                      use_bond=self._bonds() is not None, expand_edge=True,
+                                      use_bond=self._bonds() is not None, expand_edge=self._expand_edge,
                                       precision=getattr(self, "_precision", _capi.PREC_FP32),
-                                      device=dev.index or 0)
+                                      device=dev.index or 0, update_edge=self._update_edge,
+                                      batch_norm=self._batch_norm)
             self._ctx_dirty = True
         if self._ctx_dirty:
             b = self._bonds()
@@ -169,7 +175,15 @@ class _MDNetBase(nn.Module):
             raise ValueError("position and edge lists differ in length")
         sizes = [int(p.shape[0]) for p in fluid_pos_lst]
         if len(set(sizes)) != 1:
-            raise NotImplementedError("batched frames must have equal atom counts")
+            # dgl.batch of graphs of different sizes (nn_module.py:655-661) is a block-diagonal union: the frames do not
+            # interact, so one library call per frame gives the same rows
+            outs, off = [], 0
+            for p, e, n in zip(fluid_pos_lst, fluid_edge_lst, sizes):
+                if self._bonds() is not None and n != self._bond_atoms:
+                    raise ValueError("the bond list covers %d atoms, a frame has %d" % (self._bond_atoms, n))
+                outs.append(self._run([p], [e], None if feat is None else feat[off:off + n].contiguous()))
+                off += n
+            return torch.cat(outs)
         pos = torch.cat([p.float() for p in fluid_pos_lst]).contiguous()
         cs, ns, off = [], [], 0
         for e, n in zip(fluid_edge_lst, sizes):
@@ -249,8 +263,9 @@ class WaterMDDynamicBoxNet(_MDNetBase):
     and the edge direction is ``-(pos[center] - pos[neigh])`` min-imaged (:327).  ``forward(pos_lst, x, box_size_lst,
     cutoff)``; one fused library call per frame (``gamd_dynbox_forward``).
 
-    Built for the 128-wide model with LayerNorm and RBF expansion (``update_edge=False``); the 256 / 512 / 768-wide
-    DFT-water configurations of train_network_real_large.py:74-98 raise (GAMD_EUNSUPPORTED)."""
+    The 128-wide LayerNorm / RBF configuration runs on the tensor-core kernels; every other configuration - the
+    256 / 128 / 256 x 5 DFT-water model of test_nosehoover_hb.py:69-81 and wider ones (multiples of 128 up to 1024),
+    ``update_edge=True``, ``expand_edge=False``, BatchNorm - on the generic-width fp32 kernels (csrc/model_wide.cu)."""
     _kind = _capi.MODEL_DYNBOX
 
     def __init__(self, in_feats, encoding_size, out_feats, bond=None, hidden_dim=128, conv_layer=4,
@@ -259,10 +274,6 @@ class WaterMDDynamicBoxNet(_MDNetBase):
         super().__init__()
         if in_feats != 1:
             raise NotImplementedError("in_feats must be 1 (O=1 / H=0 feature)")
-        if update_edge:
-            raise NotImplementedError("update_edge=True is not built")
-        if not expand_edge:
-            raise NotImplementedError("expand_edge=False is not built")
         self.use_bond = bond is not None
         self._bond = None
         self._bond_atoms = 0
@@ -271,9 +282,9 @@ class WaterMDDynamicBoxNet(_MDNetBase):
             self._bond = b.astype(np.int64)
             self._bond_atoms = int(b.max()) + 1
         self.expand_edge = expand_edge
-        n_in = 3 + 1 + N_RBF + (1 if self.use_bond else 0)
+        n_in = 3 + 1 + (N_RBF if expand_edge else 0) + (1 if self.use_bond else 0)
         self._init_common(encoding_size, out_feats, None, hidden_dim, conv_layer, edge_embedding_dim, drop_edge,
-                          use_layer_norm, n_in)
+                          use_layer_norm, n_in, update_edge=update_edge, expand_edge=expand_edge)
         self.node_encoder = nn.Linear(in_feats, encoding_size)
         self._finish_init(encoding_size, hidden_dim, n_in)
 

@@ -18,10 +18,13 @@
  *     stream); nothing synchronises the host unless the function name ends in _host or
  *     the comment says so.
  *   - one ctx per device and per host thread; distinct ctxs are independent.
- *   - sizes the kernels are built for in this round: encoding_size = hidden_dim =
- *     edge_embedding_dim = 128 (every LJ / TIP3P / TIP4P config the reference ships,
- *     code/LJ/test_script/test_nosehoover.py:66-69, and the 128-wide dynamic-box model); other widths (the
- *     256 / 512 / 768 DFT-water models of train_network_real_large.py) return GAMD_EUNSUPPORTED.
+ *   - model shapes: encoding_size = hidden_dim = edge_embedding_dim = 128 with LayerNorm and the RBF expansion
+ *     (every LJ / TIP3P / TIP4P config the reference ships, code/LJ/test_script/test_nosehoover.py:66-69, and the
+ *     128-wide dynamic-box model) runs on the tensor-core kernels in the requested precision.  Every other shape -
+ *     widths that are multiples of 128 up to 1024 (the 256 / 128 / 256 x 5 DFT-water model of
+ *     code/water/test_script/test_nosehoover_hb.py:69-81 and wider), update_edge, expand_edge = 0, BatchNorm -
+ *     runs on a generic-width CUDA-core path in fp32 whatever precision was requested; such a context does not
+ *     take part in domain decomposition (gamd_dd_* return GAMD_EUNSUPPORTED).
  */
 #ifndef GAMD_B200_H
 #define GAMD_B200_H
@@ -79,6 +82,10 @@ typedef struct {
   int32_t use_bond;        /* 1: last edge feature is the bond flag (45 inputs) */
   int32_t expand_edge;     /* 1: 40-centre RBF expansion */
   int32_t precision;       /* GAMD_PREC_* */
+  int32_t update_edge;     /* 1: every layer replaces the edge embedding by its edge_layer_norm(e_emb)
+                              (code/nn_module.py:89-90, :139-146); needs edge_dim == encoding_size */
+  int32_t batch_norm;      /* 1: norm_layers are eval-mode BatchNorm1d (use_layer_norm=False,
+                              code/nn_module.py:193-196) instead of LayerNorm */
 } gamd_model_desc;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

@@ -31,6 +31,27 @@ def test_state_dict_keys_match_reference_layout():
     w.load_state_dict(random_state_dict(0, kind="water"))
 
 
+def test_state_dict_keys_of_the_other_variants():
+    """wide dynamic-box models, ``update_edge`` (per-layer ``edge_layer_norm`` registered first), ``expand_edge=False``
+    (no ``edge_expand.centers``, 4 edge inputs) and BatchNorm (running statistics) keep the reference's key order."""
+    from gamd_b200.nn_module import SimpleMDNetNew, WaterMDDynamicBoxNet
+    for kw in (dict(encoding_size=256, hidden_dim=128, edge_embedding_dim=256, conv_layer=5),
+               dict(encoding_size=128, hidden_dim=128, edge_embedding_dim=128, conv_layer=3, update_edge=True,
+                    expand_edge=False),
+               dict(encoding_size=768, hidden_dim=512, edge_embedding_dim=768, conv_layer=2, update_edge=True)):
+        m = WaterMDDynamicBoxNet(1, kw["encoding_size"], 3, hidden_dim=kw["hidden_dim"], conv_layer=kw["conv_layer"],
+                                 edge_embedding_dim=kw["edge_embedding_dim"], drop_edge=False, use_layer_norm=True,
+                                 update_edge=kw.get("update_edge", False), expand_edge=kw.get("expand_edge", True))
+        got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+        assert got == list(param_shapes(kind="dynbox", use_bond=False, **kw).items())
+        m.load_state_dict(random_state_dict(0, kind="dynbox", use_bond=False, **kw))
+    b = SimpleMDNetNew(128, 3, 27.27, hidden_dim=128, conv_layer=4, edge_embedding_dim=128, drop_edge=False,
+                       use_layer_norm=False)
+    got = [(k, tuple(v.shape)) for k, v in b.state_dict().items()]
+    assert got == list(param_shapes(kind="lj", use_layer_norm=False).items())
+    b.load_state_dict(random_state_dict(0, kind="lj", use_layer_norm=False))
+
+
 def test_model_on_cpu_fails_loudly():
     from gamd_b200 import _capi
     from gamd_b200.nn_module import SimpleMDNetNew

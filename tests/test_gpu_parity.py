@@ -429,3 +429,61 @@ def test_dynamic_box_model_matches_reference_golden(golden_dir, prec):
     assert np.array_equal(out2[:192], out)
     want2 = omodel.forward_dynbox(sd, [pos2.cpu().numpy()], x.cpu(), [box2], 4.2).numpy()
     check_forces("oracle:dynbox192_frame2", out2[192:], want2, prec)
+
+
+@pytest.mark.parametrize("name", ["dynbox192_w256", "dynbox192_update_edge", "dynbox96_w512", "dynbox96_w768"])
+def test_dynbox_wide_variants_golden(golden_dir, name):
+    """WaterMDDynamicBoxNet beyond the 128-wide tensor-core shape - the 256 / 128 / 256 x 5 DFT-water model of
+    code/water/test_script/test_nosehoover_hb.py:69-81, 512- and 768-wide ones, ``update_edge`` and
+    ``expand_edge=False`` - on the generic-width fp32 kernels (csrc/model_wide.cu) against goldens produced by the
+    UNMODIFIED reference module (tests/golden/make_golden.py: dynbox_variant_case)."""
+    from gamd_b200.nn_module import WaterMDDynamicBoxNet
+    from gamd_b200.weights import random_state_dict
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    D, H, De, L, upd, exp = [int(v) for v in g["dims"]]
+    model = WaterMDDynamicBoxNet(1, D, 3, hidden_dim=H, conv_layer=L, edge_embedding_dim=De, drop_edge=False,
+                                 use_layer_norm=True, update_edge=bool(upd), expand_edge=bool(exp))
+    sd = random_state_dict(int(g["seed"]), 2.9, 0.9, kind="dynbox", use_bond=False, encoding_size=D, hidden_dim=H,
+                           edge_embedding_dim=De, conv_layer=L, update_edge=bool(upd), expand_edge=bool(exp))
+    model.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    model.cuda().eval()
+    n = g["pos"].shape[0]
+    pos = torch.as_tensor(g["pos"], device=DEV)
+    x = torch.zeros(n, 1, device=DEV)
+    x[::3] = 1.0
+    out = model([pos], x, [g["box"]], 4.2).cpu().numpy()
+    check_forces("golden:" + name, out, g["force"], "fp32")
+    # a larger frame (many tiles, receiver runs cut by tile boundaries) against the oracle
+    rng = np.random.Generator(np.random.PCG64(21))
+    n2 = 960
+    pos2 = rng.uniform(0.0, 24.0, (n2, 3)).astype(np.float32)
+    box2 = np.array([24.0, 25.0, 23.5], dtype=np.float32)
+    x2 = torch.zeros(n2, 1, device=DEV)
+    x2[::3] = 1.0
+    out2 = model([torch.as_tensor(pos2, device=DEV)], x2, [box2], 4.2).cpu().numpy()
+    want2 = omodel.forward_dynbox(sd, [pos2], x2.cpu(), [box2], 4.2).numpy()
+    check_forces("oracle:" + name + "_960", out2, want2, "fp32")
+
+
+def test_lj_batchnorm_golden_and_unequal_frames(golden_dir):
+    """``use_layer_norm=False``: eval-mode BatchNorm1d node normalisation (nn_module.py:193-196) against the reference's
+    own output; and a batch of frames of different sizes (dgl.batch, nn_module.py:655-661) equals the single frames."""
+    from gamd_b200.nn_module import SimpleMDNetNew
+    from gamd_b200.weights import random_state_dict
+    g = np.load(os.path.join(golden_dir, "lj258_batchnorm.npz"))
+    m = SimpleMDNetNew(128, 3, 27.27, hidden_dim=128, conv_layer=4, edge_embedding_dim=128, drop_edge=False,
+                       use_layer_norm=False)
+    m.load_state_dict(random_state_dict(int(g["seed"]), float(g["length_mean"]), float(g["length_std"]), kind="lj",
+                                        use_layer_norm=False))
+    m.cuda().eval()
+    p = g["pos"][0]
+    e = torch.from_numpy(onb.edges_bruteforce(p, 27.27, 7.5)).to(DEV)
+    out = m([torch.as_tensor(p, device=DEV)], [e]).cpu().numpy()
+    check_forces("golden:lj258_batchnorm", out, g["force"], "fp32")
+    # unequal frames: 258 atoms and its first 200 atoms
+    p2 = p[:200]
+    e2 = torch.from_numpy(onb.edges_bruteforce(p2, 27.27, 7.5)).to(DEV)
+    both = m([torch.as_tensor(p, device=DEV), torch.as_tensor(p2, device=DEV)], [e, e2]).cpu().numpy()
+    single2 = m([torch.as_tensor(p2, device=DEV)], [e2]).cpu().numpy()
+    assert both.shape == (458, 3)
+    assert np.array_equal(both[:258], out) and np.array_equal(both[258:], single2)
