@@ -69,8 +69,11 @@ class System:
 
 
 class State:
-    def __init__(self, x=None, v=None, ke=None):
-        self._x, self._v, self._ke = x, v, ke
+    def __init__(self, x=None, v=None, ke=None, time_ps=None):
+        self._x, self._v, self._ke, self._t = x, v, ke, time_ps
+
+    def getTime(self):
+        return self._t
 
     def getPositions(self, asNumpy=True):
         return self._x
@@ -147,7 +150,7 @@ class Context:
             v = self.v.cpu().numpy()
         if getEnergy:
             ke = self.kinetic_energy()
-        return State(x, v, ke)
+        return State(x, v, ke, getattr(self, "time_ps", 0.0))
 
 
 class _HackIntegrator:
@@ -439,20 +442,53 @@ class CompoundIntegrator:
 
 
 class Simulation:
-    """``Simulation(topology, system, integrator)``: only ``context``, ``step`` and ``reporters``."""
+    """``Simulation(topology, system, integrator)``: ``context``, ``step``, ``currentStep`` and ``reporters``.
+
+    Reporters follow OpenMM's protocol (``describeNextReport(simulation)`` -> steps until the next report and what the
+    State must hold; ``report(simulation, state)``), e.g. ``gamd_b200.openmm_adapter.StateDataReporter``; a plain
+    callable is called with the simulation after every ``step`` call.  As in OpenMM, the clock advances by the current
+    integrator's step size per step - the reference's two half-step programs therefore make ``Step`` and ``Time`` run
+    twice as fast as the MD step count (code/LJ/test_script/test_langevin.py:79-82)."""
 
     def __init__(self, topology, system, integrator, platform=None, device="cuda:0"):
-        self.system, self.integrator = system, integrator
+        self.topology, self.system, self.integrator = topology, system, integrator
         self.context = Context(system, device)
+        self.context.time_ps = 0.0
         integrator.bind(self.context)
         self.reporters = []
         self.currentStep = 0
 
+    @property
+    def time_ps(self):
+        return self.context.time_ps
+
+    def _dt(self):
+        cur = self.integrator
+        if isinstance(cur, CompoundIntegrator):
+            cur = cur._ints[cur.getCurrentIntegrator()]
+        return cur.getStepSize() if hasattr(cur, "getStepSize") else 0.0
+
     def step(self, n=1):
-        self.integrator.step(n)
-        self.currentStep += n
+        remaining = int(n)
+        while remaining > 0:
+            nxt, due = remaining, []
+            for r in self.reporters:
+                if hasattr(r, "describeNextReport"):
+                    d = r.describeNextReport(self)
+                    if d[0] < nxt:
+                        nxt, due = d[0], [(r, d)]
+                    elif d[0] == nxt:
+                        due.append((r, d))
+            self.integrator.step(nxt)
+            self.currentStep += nxt
+            self.context.time_ps += nxt * self._dt()
+            remaining -= nxt
+            for r, d in due:
+                st = self.context.getState(getPositions=bool(d[1]), getVelocities=bool(d[2]), getEnergy=bool(d[4]))
+                r.report(self, st)
         for r in self.reporters:
-            r(self)
+            if not hasattr(r, "describeNextReport"):
+                r(self)
 
     def minimizeEnergy(self, *a, **k):
         """no-op: there is no classical potential in the GNN-driven loop"""
