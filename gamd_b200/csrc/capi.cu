@@ -319,10 +319,14 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   // GAMD_WAIT_SLEEP_NS: poll the accumulator barrier with __nanosleep(ns) between attempts instead
   if (const char* e = getenv("GAMD_WAIT_SLEEP_NS")) ctx->wait_hint_ns = (int)(0x80000000u | (uint32_t)(atoi(e) & 0xffff));
   if (const char* e = getenv("GAMD_MP_ROW_PREFETCH")) ctx->mp_row_prefetch = atoi(e);
+  if (const char* e = getenv("GAMD_MP_TWEAK")) ctx->mp_tweak = atoi(e);
   ctx->dd_reserve_sms = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
-  // message-passing edge kernel: 6 = CTA pairs (cta_group::2), resident weights, three tiles in flight (default);
-  // 5 = the same with a commit wait between GEMMs; 3 / 4 = three tiles, single CTA; 0 = the round-1 two-tile kernel
-  ctx->mp_variant = getenv("GAMD_MP_VARIANT") ? atoi(getenv("GAMD_MP_VARIANT")) : 8;
+  // message-passing edge kernel: CTA pairs (cta_group::2), resident weights, three tiles in flight - 11 = fixed service
+  // order in the leader, accumulator block known to the epilogue threads without a published hand-over (default);
+  // 8 = dynamic order, single-round-trip tile set-up; 9 / 10 = 8 with the SiLU exponential on the FMA pipe; 6 = 8 with
+  // the two-round-trip set-up; 7 = N-split GEMMs; 5 = 6 with a commit wait between GEMMs; 3 / 4 = three tiles, single
+  // CTA; 0 = the round-1 two-tile kernel
+  ctx->mp_variant = getenv("GAMD_MP_VARIANT") ? atoi(getenv("GAMD_MP_VARIANT")) : 11;
   // neighbor candidate reuse: skin as a fraction of the cutoff (reference: 1/6); GAMD_NBR_SKIN=0 rebuilds every step
   ctx->vl_skin_frac = getenv("GAMD_NBR_SKIN") ? (float)atof(getenv("GAMD_NBR_SKIN")) : (1.f / 6.f);
   if (getenv("GAMD_NBR_SKIN_MIN_ATOMS")) ctx->vl_min_atoms = atoll(getenv("GAMD_NBR_SKIN_MIN_ATOMS"));

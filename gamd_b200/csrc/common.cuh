@@ -131,6 +131,7 @@ struct gamd_ctx {
   float* dd_push_rows[2] = {nullptr, nullptr};
   int64_t dd_push_n = 0;
   int mp_row_prefetch = 0;   // GAMD_MP_ROW_PREFETCH
+  int mp_tweak = 0;          // GAMD_MP_TWEAK: development switches of the MP pair kernel
   int wait_hint_ns = 0;   // GAMD_WAIT_HINT_NS: mbarrier try_wait suspend-time hint in the tensor kernels' epilogues
   int mp_variant = 0;
   int enc_variant = 3;         // edge encoder: 3 = three tiles in flight (in-place TMEM operands), 0 = two tiles

@@ -572,7 +572,7 @@ int mp_edge_tc_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which) {
   const bool tiny = ctx->model_atoms > 0 && ctx->model_atoms <= ctx->mp_small_atoms;
   // 7 = 6 with every GEMM issued as two N = 64 halves (separate commits: the epilogue starts on the first half)
   // 8 = 6 with the one-round-trip tile set-up (hi part through the staging rows, lo part through registers)
-  if (ctx->mp_variant >= 5 && ctx->mp_variant <= 10 && !tiny)
+  if (ctx->mp_variant >= 5 && ctx->mp_variant <= 12 && !tiny)
     return mp_edge_tc2_launch(ctx, layer, st, which, ctx->mp_variant == 5, ctx->mp_variant == 7);
   const size_t smem = sizeof(SmemTC) + 1024;
   if (!(ctx->attr_mask & GAMD_ATTR_MP_TC)) {

@@ -70,6 +70,8 @@ struct MpTcArgs {
   int row_prefetch;        // L2 prefetch of the tile's sender rows at tile start (GAMD_MP_ROW_PREFETCH)
   uint32_t wait_hint_ns;   // suspend-time hint of the epilogue warps' accumulator waits (0 = plain poll loop)
   long long* dbg;   // development: clock64 timeline of CTA 0 (nullptr = off)
+  int tweak;        // development (GAMD_MP_TWEAK): 1 e-tile lo part loaded without L1 allocation, 2 first dst_affine chunk
+                    // row prefetched into L1 before the stage-1 accumulator wait
 };
 
 __device__ __forceinline__ long long gtime() {   // nanoseconds, comparable across SMs (clock64 is per SM)
@@ -101,6 +103,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ float lds32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_na(const uint4* p) {   // streaming read: do not displace the L1-resident dst_affine rows
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem) {
@@ -388,7 +395,17 @@ __device__ __forceinline__ void stage_epilogue(const EpiCtx& c) {
   }
 }
 
-template <bool SAFE_WAR, bool NSPLIT, bool SETUP1, int POLY = 0>
+// STATIC: the leader serves the slots in a fixed round-robin order (slot 0, 1, 2 of stage s, then stage s + 1 ...) instead
+// of "whichever is ready".  GEMM number n of a CTA pair then always writes TMEM block (3 + n) & 3, so every epilogue
+// thread knows its accumulator block from (stage, slot, slots active in its group) alone: the leader no longer publishes
+// the block through shared memory of both CTAs (remote store + cluster fence per GEMM) and polls ONE barrier at CTA
+// scope instead of three at cluster scope - 0.55 us of leader time per GEMM, which paced the whole pair (the slots
+// run in lock step, twelve GEMMs back to back per tile round: profiles/experiments/README.md).
+// STAMP: dynamic service order (whichever slot is ready), but the block hand-over carries a sequence stamp instead of
+// being ordered by a cluster fence: the leader writes (GEMM count of the slot << 8 | block) to both CTAs' shared memory
+// with plain stores, an epilogue thread re-reads it until the stamp is the one it expects (normally at once: the store
+// is more than a microsecond older than the commit that releases the thread); the leader polls at CTA scope.
+template <bool SAFE_WAR, bool NSPLIT, bool SETUP1, int POLY = 0, bool STATIC = false, bool STAMP = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edge_tc2(MpTcArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
   SmemTC& sm = *reinterpret_cast<SmemTC*>(raw);
@@ -470,9 +487,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
       return a.tile_list ? __ldg(a.tile_list + slot) : slot;
     };
     int next_tile = tile_of(cid * NSLOT + g);
+    uint32_t nstage = 0;     // GEMMs of my slot so far (the stamp of the block hand-over, STAMP kernels)
     for (int grp = cid; grp < ngroups; grp += ncl) {
       const int sslot = grp * NSLOT + g;
       if (sslot >= nsuper) continue;
+      const uint32_t nact = (uint32_t)min(NSLOT, nsuper - grp * NSLOT);   // slots at work in this group (< NSLOT: tail)
       const int tile = next_tile;
       const bool dbg_on = dbg_rec && cid == 0 && lane == 0 && dbg_n + 14 <= 256;
       if (dbg_on) dbg_rec[dbg_n++] = gtime();
@@ -507,7 +526,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
         if (exact) {
           uint4 ql[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) ql[i] = __ldg(bh + 32768 / 16 + chunk_of(i) * 128);
+          for (int i = 0; i < 8; i++)
+            ql[i] = (a.tweak & 1) ? ldg_na(bh + 32768 / 16 + chunk_of(i) * 128) : __ldg(bh + 32768 / 16 + chunk_of(i) * 128);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const uint32_t l[8] = {ql[2 * j].x, ql[2 * j].y, ql[2 * j].z, ql[2 * j].w,
@@ -612,10 +632,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
       // times per tile)
 #define GAMD_STAGE(S)                              \
   if (dbg_on) dbg_rec[dbg_n++] = gtime();        \
+  if (S == 1 && (a.tweak & 2)) {                   \
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(c.dst_row)); \
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(c.dst_row + 8)); \
+  }                                                \
   mbar_wait_hint(d_bar, d_par, a.wait_hint_ns);    \
   d_par ^= 1;                                      \
   tc_fence_after();                                \
-  c.Dc = tb + lane_base + sm.home[g] * 128u;       \
+  nstage++;                                        \
+  if (STAMP) {                                     \
+    uint32_t hv = sm.home[g];                      \
+    while ((hv >> 8) != nstage) hv = sm.home[g];   \
+    c.Dc = tb + lane_base + (hv & 0xffu) * 128u;   \
+  } else {                                         \
+    c.Dc = tb + lane_base + (STATIC ? ((3u + S * nact + (uint32_t)g) & 3u) : sm.home[g]) * 128u; \
+  }                                                \
   c.d_par1 = d_par ^ 1u;                           \
   if (dbg_on) dbg_rec[dbg_n++] = gtime();        \
   if (exact) stage_epilogue<S, true, NSPLIT, POLY>(c);   \
@@ -627,12 +658,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
     if (lane == 0) mbar_arrive_cluster_relaxed(a_bar); \
   }                                                \
   if (dbg_on) dbg_rec[dbg_n++] = gtime();
-      GAMD_STAGE(0)
-      GAMD_STAGE(1)
-      GAMD_STAGE(2)
-      GAMD_STAGE(3)
+      { GAMD_STAGE(0) }
+      { GAMD_STAGE(1) }
+      { GAMD_STAGE(2) }
+      { GAMD_STAGE(3) }
 #undef GAMD_STAGE
     }
+  } else if (STATIC && warp == MMA_WARP && rank == 0) {
+    // ===================== MMA issue for the CTA pair, fixed service order =====================
+    const uint32_t leader = elect_leader();
+    const uint32_t idesc = umma_idesc_bf16(256, 128);
+    const int n_my_groups = cid < ngroups ? (ngroups - 1 - cid) / ncl + 1 : 0;
+    const uint32_t wbase = smem_u32(&sm.w[0][0][0]);
+    uint32_t a_par_bits = 0;                  // bit g: parity of slot g's next A-ready phase
+    uint32_t home[NSLOT];
+#pragma unroll
+    for (int g = 0; g < NSLOT; g++) home[g] = g;
+    uint32_t n = 0;                           // GEMMs issued so far: GEMM n writes block (3 + n) & 3
+    long long* dbg_rec = (a.dbg && cid == 0) ? a.dbg + MMA_WARP * 256 : nullptr;
+    int dbg_n = 0;
+    for (int i = 0; i < n_my_groups; i++) {
+      const int grp = cid + i * ncl;
+      const int nact = min(NSLOT, nsuper - grp * NSLOT);
+#pragma unroll 1
+      for (int s = 0; s < 4; s++) {
+        const uint32_t bhi = wbase + (uint32_t)(s * 2) * WPART;
+        const uint64_t dsc = umma_desc_sw128(bhi);
+        const uint32_t dhi = (uint32_t)(dsc >> 32);
+        const uint32_t dlo_hi = (uint32_t)dsc, dlo_lo = dlo_hi + (WPART >> 4);
+#pragma unroll
+        for (int g = 0; g < NSLOT; g++) {
+          if (g >= nact) continue;
+          uint32_t spins = 0;
+          while (!__all_sync(0xffffffffu, mbar_test_wait(&sm.a_ready[g], (a_par_bits >> g) & 1u)))
+            if (++spins > (1u << 26)) __trap();
+          a_par_bits ^= 1u << g;
+          tc_fence_after();
+          const bool dbg_on = dbg_rec && lane == 0 && dbg_n + 3 <= 256;
+          if (dbg_on) {
+            dbg_rec[dbg_n++] = g * 4 + s;
+            dbg_rec[dbg_n++] = gtime();
+          }
+          const uint32_t blk = (3u + n) & 3u;
+          const uint32_t d = tb + blk * 128u, ab = tb + home[g] * 128u;
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++)     // A_hi * B_hi
+            umma_ts2_elect_lh(d, ab + ks * 16, dlo_hi + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, ks ? 1u : 0u, leader);
+          if (a.exact) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++)   // A_lo * B_hi
+              umma_ts2_elect_lh(d, ab + 8 + ks * 16, dlo_hi + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, 1u, leader);
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++)   // A_hi * B_lo
+              umma_ts2_elect_lh(d, ab + ks * 16, dlo_lo + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, dhi, idesc, 1u, leader);
+          }
+          if (leader) umma_commit2_mc(&sm.d_ready[g][0], (uint16_t)3);
+          __syncwarp();
+          if (dbg_on) dbg_rec[dbg_n++] = gtime();
+          home[g] = blk;
+          n++;
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == MMA_WARP && rank == 0) {
     // ===================== MMA issue for the CTA pair: an event loop over the tiles in flight =====================
     // Each slot walks its own sequence of (group, stage) steps Q = 4 * group_iteration + stage and is served as soon
@@ -697,7 +785,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
             continue;
           }
           if (!war_ok) continue;
-          if (!__all_sync(0xffffffffu, mbar_test_wait_cluster(&sm.a_ready[g], a_par[g]))) continue;
+          if (!__all_sync(0xffffffffu, STAMP ? mbar_test_wait(&sm.a_ready[g], a_par[g])
+                                                 : mbar_test_wait_cluster(&sm.a_ready[g], a_par[g]))) continue;
           int pr = g - first;
           if (pr < 0) pr += NSLOT;
           if (pr < best) {
@@ -719,9 +808,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
           const uint32_t bhi = wbase + (uint32_t)(s * 2) * WPART;      // [hi | lo] images of stage s, WPART apart
           const uint32_t d = tb + floating * 128u, ab = tb + home[g] * 128u;
           if (leader) {       // read by the slot's epilogue threads (both CTAs) after the commit arrives
-            sm.home[g] = floating;
-            st_cluster_u32(home_peer[g], floating);
-            fence_acq_rel_cluster();
+            if (STAMP) {
+              const uint32_t hv = ((uint32_t)(Qg[g] + 1) << 8) | floating;
+              sm.home[g] = hv;
+              st_cluster_u32(home_peer[g], hv);
+            } else {
+              sm.home[g] = floating;
+              st_cluster_u32(home_peer[g], floating);
+              fence_acq_rel_cluster();
+            }
           }
           __syncwarp();
           // 24 (bf16x3) or 8 (bf16) MMAs per N part, fully unrolled: per MMA only the TMEM column of A and the
@@ -785,6 +880,8 @@ int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, boo
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GAMD_CUDA(cudaFuncSetAttribute(k_mp_edge_tc2<false, false, true, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->attr_mask |= GAMD_ATTR_MP_TC2;
   }
   MpTcArgs a;
@@ -805,13 +902,16 @@ int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, boo
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
   a.wait_hint_ns = (uint32_t)ctx->wait_hint_ns;
   a.row_prefetch = ctx->mp_row_prefetch;
+  a.tweak = ctx->mp_tweak;
   a.dbg = (ctx->dbg_timeline && layer == 1) ? reinterpret_cast<long long*>(ctx->e_emb + (size_t)ctx->cap_edges * 128) : nullptr;
   // interior launch of a tile-split layer: optionally leave a few SMs to the halo exchange running beside it
   const int reserve = ctx->dd_reserve_sms;
   int grid = which == 0 && reserve > 0 && reserve < ctx->sm_count ? ctx->sm_count - reserve : ctx->sm_count;
   grid &= ~1;       // whole CTA pairs
   // nsplit needs the N-split row order of the pair weight images (capi.cu builds them by ctx->mp_variant)
-  if (ctx->mp_variant == 9) k_mp_edge_tc2<false, false, true, 1><<<grid, THREADS, smem, st>>>(a);
+  if (ctx->mp_variant == 11) k_mp_edge_tc2<false, false, true, 0, true><<<grid, THREADS, smem, st>>>(a);
+  else if (ctx->mp_variant == 12) k_mp_edge_tc2<false, false, true, 0, false, true><<<grid, THREADS, smem, st>>>(a);
+  else if (ctx->mp_variant == 9) k_mp_edge_tc2<false, false, true, 1><<<grid, THREADS, smem, st>>>(a);
   else if (ctx->mp_variant == 10) k_mp_edge_tc2<false, false, true, 2><<<grid, THREADS, smem, st>>>(a);
   else if (ctx->mp_variant == 8) k_mp_edge_tc2<false, false, true><<<grid, THREADS, smem, st>>>(a);
   else if (nsplit) k_mp_edge_tc2<false, true, false><<<grid, THREADS, smem, st>>>(a);
