@@ -96,7 +96,10 @@ MP_KERNELS = {   # GAMD_MP_VARIANT -> (kernel name, sources)
     3: ("k_mp_edge_tc3", ["mp_tc3.cu", "tc_common.cuh"]), 4: ("k_mp_edge_tc3", ["mp_tc3.cu", "tc_common.cuh"]),
     5: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]), 6: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]),
     7: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]), 8: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]),
+    9: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]), 10: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]),
+    11: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]), 12: ("k_mp_edge_tc2", ["mp_tc2cta.cu", "tc_common.cuh"]),
 }
+MP_DEFAULT_VARIANT = 11   # the library's default (capi.cu: gamd_create)
 
 
 def measured_traffic(workload, precision, kernel, sources):
@@ -119,7 +122,7 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -128,12 +131,19 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "25"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    @staticmethod
+    def mark():
+        """wall-clock mark: the sampler is started before the warm-up (nvidia-smi needs a few hundred ms to deliver its
+        first line) and the timed region is cut out of its log by the samples' own time stamps"""
+        import time
+        return time.time()
+
+    def stop(self, begin=0.0, end=None):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -144,9 +154,24 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
+        import datetime
+        lines = self.f.read().splitlines()
+
+        def in_window(line):
+            try:
+                t = datetime.datetime.strptime(line.split(",")[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                return True
+            return t >= begin and (end is None or t <= end)
+        window = [l for l in lines if in_window(l)] if begin else lines
+        if begin and len(window) < 2:
+            # a timed region shorter than two sampling periods: fall back to every sample taken under the same load
+            # (warm-up steps included) and say so
+            window = lines
+            out["window"] = "warmup+timed"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
+        for line in window:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
@@ -373,24 +398,41 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident arm ----
+    sampler = ClockSampler(local) if rank == 0 else None
     run_steps(args.warmup)
     ctx.check_async_errors()
-    ctx.profile_enable(True)
-    for st in ("neighbor", "edge_encode", "mp_edge", "node_update", "integrate"):
-        ctx.profile_read(st)
+    # per-stage CUDA-event timers run inside the timed region for the large systems (the roofline's launch time comes
+    # from exactly the timed launches).  They switch off the CUDA-graph replay of launch-bound systems (<= 200 k atoms),
+    # so those are timed as a user runs them - graph replay, no timers - and their stage breakdown comes from a separate
+    # short pass afterwards
+    STAGES = ("neighbor", "edge_encode", "mp_edge", "node_update", "integrate")
+    profile_in_timed = mode == "dd" or n > 200000
+    if profile_in_timed:
+        ctx.profile_enable(True)
+        for st in STAGES:
+            ctx.profile_read(st)
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
+    mark0 = sampler.mark() if sampler else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     run_steps(args.steps)
     e1.record()
     barrier()
+    mark1 = sampler.mark() if sampler else 0
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(mark0, mark1) if sampler else None
     ctx.check_async_errors()
-    stages = {st: ctx.profile_read(st) for st in ("neighbor", "edge_encode", "mp_edge", "node_update", "integrate")}
+    prof_steps = args.steps
+    if not profile_in_timed:
+        ctx.profile_enable(True)
+        for st in STAGES:
+            ctx.profile_read(st)
+        prof_steps = max(4, min(args.steps, 20))
+        run_steps(prof_steps)
+        torch.cuda.synchronize()
+    stages = {st: ctx.profile_read(st) for st in STAGES}
     ctx.profile_enable(False)
 
     # ---- end-to-end arm: host buffers, pinned, copies inside the timed region ----
@@ -461,8 +503,8 @@ def run_ours(args):
     mp_avg_s = mp_ms / max(mp_cnt, 1) * 1e-3
     flop_per_launch = 131072.0 * n_edges            # 4 x (128x128) mat-vec per edge
     achieved = flop_per_launch / mp_avg_s / 1e12 if mp_avg_s > 0 else 0.0
-    mp_variant = int(os.environ.get("GAMD_MP_VARIANT", "8"))       # the library's default (capi.cu)
-    mp_kernel, mp_sources = MP_KERNELS.get(mp_variant, MP_KERNELS[8]) if args.precision != "fp32" else ("k_mp_edge", ["model_fp32.cu"])
+    mp_variant = int(os.environ.get("GAMD_MP_VARIANT", str(MP_DEFAULT_VARIANT)))
+    mp_kernel, mp_sources = MP_KERNELS.get(mp_variant, MP_KERNELS[MP_DEFAULT_VARIANT]) if args.precision != "fp32" else ("k_mp_edge", ["model_fp32.cu"])
     traffic = measured_traffic(args.workload, args.precision, mp_kernel, mp_sources) if world == 1 else None
     # the other stages against their own bound: encoder 76 800 FLOP / 516 B per edge, neighbor search
     # 60 N + 4 E bytes, node update 163 840 FLOP per node and layer (+ 33 536 decoder)
@@ -500,7 +542,9 @@ def run_ours(args):
                    "l2": "working set (edge embeddings %.1f GB) is larger than L2" % (n_edges * 512 / 1e9)
                    if n_edges * 512 > 2e8 else "working set fits L2 (latency-bound system)"},
         "edges_per_s_per_layer": n_edges / mp_avg_s if mp_avg_s > 0 else None,
-        "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+        "stage_ms_per_step": {k: v[0] / prof_steps for k, v in stages.items()},
+        "stage_timers": "inside the timed region" if profile_in_timed else
+                        f"separate pass of {prof_steps} steps (the timers switch off CUDA-graph replay)",
         "roofline": {"bound": "tensor",
                      "kernel": mp_kernel + " (message-passing edge chain + segmented reduce)",
                      # algorithmic FLOPs: 4 x (128x128) mat-vec per edge = 131072; the bf16x3 mode

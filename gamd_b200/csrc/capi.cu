@@ -319,7 +319,6 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
   // GAMD_WAIT_SLEEP_NS: poll the accumulator barrier with __nanosleep(ns) between attempts instead
   if (const char* e = getenv("GAMD_WAIT_SLEEP_NS")) ctx->wait_hint_ns = (int)(0x80000000u | (uint32_t)(atoi(e) & 0xffff));
   if (const char* e = getenv("GAMD_MP_ROW_PREFETCH")) ctx->mp_row_prefetch = atoi(e);
-  if (const char* e = getenv("GAMD_MP_TWEAK")) ctx->mp_tweak = atoi(e);
   ctx->dd_reserve_sms = getenv("GAMD_DD_RESERVE_SMS") ? atoi(getenv("GAMD_DD_RESERVE_SMS")) : 0;
   // message-passing edge kernel: CTA pairs (cta_group::2), resident weights, three tiles in flight - 11 = fixed service
   // order in the leader, accumulator block known to the epilogue threads without a published hand-over (default);

@@ -131,10 +131,10 @@ struct gamd_ctx {
   float* dd_push_rows[2] = {nullptr, nullptr};
   int64_t dd_push_n = 0;
   int mp_row_prefetch = 0;   // GAMD_MP_ROW_PREFETCH
-  int mp_tweak = 0;          // GAMD_MP_TWEAK: development switches of the MP pair kernel
   int wait_hint_ns = 0;   // GAMD_WAIT_HINT_NS: mbarrier try_wait suspend-time hint in the tensor kernels' epilogues
   int mp_variant = 0;
-  int enc_variant = 3;         // edge encoder: 3 = three tiles in flight (in-place TMEM operands), 0 = two tiles
+  int enc_variant = 4;         // edge encoder: 4 = three tiles in flight, fixed service order (default); 3 = the same with
+                               // the dynamic event loop; 0 = two tiles
   int64_t model_atoms = 0;     // atoms of the forward pass in flight (model_begin)
   // generic-width fp32 path (model_wide.cu): widths other than 128, update_edge, no RBF expansion, BatchNorm
   bool wide = false;

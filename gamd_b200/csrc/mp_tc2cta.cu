@@ -70,8 +70,6 @@ struct MpTcArgs {
   int row_prefetch;        // L2 prefetch of the tile's sender rows at tile start (GAMD_MP_ROW_PREFETCH)
   uint32_t wait_hint_ns;   // suspend-time hint of the epilogue warps' accumulator waits (0 = plain poll loop)
   long long* dbg;   // development: clock64 timeline of CTA 0 (nullptr = off)
-  int tweak;        // development (GAMD_MP_TWEAK): 1 e-tile lo part loaded without L1 allocation, 2 first dst_affine chunk
-                    // row prefetched into L1 before the stage-1 accumulator wait
 };
 
 __device__ __forceinline__ long long gtime() {   // nanoseconds, comparable across SMs (clock64 is per SM)
@@ -527,7 +525,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
           uint4 ql[8];
 #pragma unroll
           for (int i = 0; i < 8; i++)
-            ql[i] = (a.tweak & 1) ? ldg_na(bh + 32768 / 16 + chunk_of(i) * 128) : __ldg(bh + 32768 / 16 + chunk_of(i) * 128);
+            ql[i] = ldg_na(bh + 32768 / 16 + chunk_of(i) * 128);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const uint32_t l[8] = {ql[2 * j].x, ql[2 * j].y, ql[2 * j].z, ql[2 * j].w,
@@ -632,7 +630,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
       // times per tile)
 #define GAMD_STAGE(S)                              \
   if (dbg_on) dbg_rec[dbg_n++] = gtime();        \
-  if (S == 1 && (a.tweak & 2)) {                   \
+  if (S == 1) {   /* my receiver's dst_affine half row (two lines) into L1 underneath the wait */ \
     asm volatile("prefetch.global.L1 [%0];" ::"l"(c.dst_row)); \
     asm volatile("prefetch.global.L1 [%0];" ::"l"(c.dst_row + 8)); \
   }                                                \
@@ -902,7 +900,6 @@ int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, boo
   a.exact = ctx->desc.precision == GAMD_PREC_BF16X3 ? 1 : 0;
   a.wait_hint_ns = (uint32_t)ctx->wait_hint_ns;
   a.row_prefetch = ctx->mp_row_prefetch;
-  a.tweak = ctx->mp_tweak;
   a.dbg = (ctx->dbg_timeline && layer == 1) ? reinterpret_cast<long long*>(ctx->e_emb + (size_t)ctx->cap_edges * 128) : nullptr;
   // interior launch of a tile-split layer: optionally leave a few SMs to the halo exchange running beside it
   const int reserve = ctx->dd_reserve_sms;
