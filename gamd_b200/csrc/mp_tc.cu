@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
       mbar_init(&sm.empty[i], 2);   // both tile slots must have consumed a weight stage before it is replaced
     }
     for (int g = 0; g < 2; g++) {
-      mbar_init(&sm.a_ready[g], 256);
+      mbar_init(&sm.a_ready[g], 8);        // one arrival per epilogue warp of the tile
       mbar_init(&sm.d_ready[g], 1);
     }
     fence_barrier_init();
@@ -417,7 +417,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(a_bar);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_bar);
       }
       if (dbg_on) dbg_rec[dbg_n++] = clock64();
 
@@ -447,7 +448,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
   if (S < 3) {                                     \
     tmem_wait_st();                                \
     tc_fence_before();                             \
-    mbar_arrive(a_bar);                            \
+    __syncwarp();                                  \
+    if (lane == 0) mbar_arrive(a_bar);             \
   }                                                \
   if (dbg_on) dbg_rec[dbg_n++] = clock64();
       GAMD_STAGE(0)

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
       mbar_init(&sm.empty[i], 1);
     }
     for (int g = 0; g < 2; g++) {
-      mbar_init(&sm.a_ready[g], 256);
+      mbar_init(&sm.a_ready[g], 8);        // one arrival per epilogue warp of the tile
       mbar_init(&sm.d_ready[g], 1);
     }
     fence_barrier_init();
@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
     auto signal_A = [&]() {
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(a_bar);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_bar);
     };
     auto wait_D = [&]() {
       mbar_wait(d_bar, d_par);
@@ -406,7 +407,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
           // D of this slot is free again (A = hn stays): lets the MMA warp start the next affine / next tile
           if (k < 2) {
             tc_fence_before();
-            mbar_arrive(a_bar);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_bar);
           }
         }
       } else {
