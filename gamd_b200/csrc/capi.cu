@@ -272,8 +272,10 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
                    (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
     return GAMD_ENOGPU;
   }
+  // GAMD_FORCE_WIDE=r (development): run a 128-wide model on the generic-width fp32 kernels with tiles of 16 r rows
+  const int force_wide = getenv("GAMD_FORCE_WIDE") ? atoi(getenv("GAMD_FORCE_WIDE")) : 0;
   const bool wide = desc->encoding_size != GAMD_NF || desc->hidden_dim != GAMD_NF || desc->edge_dim != GAMD_NF ||
-                    desc->update_edge || desc->batch_norm || !desc->expand_edge;
+                    desc->update_edge || desc->batch_norm || !desc->expand_edge || force_wide > 0;
   int wide_r = 4, wide_xs = GAMD_NF + 4;
   if (wide) {
     for (int v : {desc->encoding_size, desc->hidden_dim, desc->edge_dim})
@@ -289,6 +291,7 @@ int gamd_create(int device, const gamd_model_desc* desc, gamd_ctx** out) {
       g_create_err = "model too wide for the shared-memory tiles";
       return GAMD_EUNSUPPORTED;
     }
+    if (force_wide == 1 || force_wide == 2 || force_wide == 4) wide_r = force_wide < wide_r ? force_wide : wide_r;
   }
   if (desc->conv_layer < 1 || desc->conv_layer > 8) {
     g_create_err = "conv_layer must be in 1..8";

@@ -102,8 +102,11 @@ struct RowIO {
   float* push_rows[2];
 };
 
-// 16 columns [col0 + cc*16, +16) of my warp's 32 rows of a row-major [n,128] fp32 matrix -> x[16] of my row
-__device__ __forceinline__ void load_rows(const RowIO& io, const float* __restrict__ M, int cc, float (&x)[16]) {
+// 16 columns [col0 + cc*16, +16) of my warp's 32 rows of a row-major [n,128] fp32 matrix -> x[16] of my row,
+// in two halves, so that the copy of the next chunk runs underneath the arithmetic on the current one (and the
+// first chunk of a phase underneath the GEMM that precedes it): issue_rows starts the copy into my warp's inbound tile,
+// take_rows waits for it and reads my row.  One copy in flight per warp: issue the next one only after take_rows.
+__device__ __forceinline__ void issue_rows(const RowIO& io, const float* __restrict__ M, int cc) {
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; it++) {
@@ -111,7 +114,10 @@ __device__ __forceinline__ void load_rows(const RowIO& io, const float* __restri
     row = row < io.n_atoms ? row : io.n_atoms - 1;
     cp_async16s(io.in_buf + io.l_off + it * 8 * GROW, M + (size_t)row * 128 + io.col0 + cc * 16 + io.l_col);
   }
-  cp_async_commit_wait();
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void take_rows(const RowIO& io, float (&x)[16]) {
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   __syncwarp();
 #pragma unroll
   for (int j4 = 0; j4 < 4; j4++) {
@@ -328,21 +334,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
         layer_norm_to_A();
         signal_A();
       } else {
-        // A <- agg rows
+        // A <- agg rows (the copy of chunk cc + 1 runs underneath the split / TMEM store of chunk cc)
+        issue_rows(io, a.agg, 0);
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
           float x[16];
-          load_rows(io, a.agg, cc, x);
+          take_rows(io, x);
+          if (cc < 3) issue_rows(io, a.agg, cc + 1);
           write_A(cc, x);
         }
         signal_A();
+        issue_rows(io, a.pd, 0);                   // first phi_dst chunk underneath the phi_edge GEMM
         // phi_edge(agg) + b + phi_dst(hn_prev) -> SiLU -> A
         wait_D();
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
           float x[16], p[16];
           load_D(cc, x);
-          load_rows(io, a.pd, cc, p);
+          take_rows(io, p);
+          if (cc < 3) issue_rows(io, a.pd, cc + 1);
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
             const float4 b = bias_at(0, cc, j4);
@@ -354,13 +364,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_node_tc(NodeTcArgs a) {
           write_A(cc, x);
         }
         signal_A();
+        issue_rows(io, a.h, 0);                    // first residual chunk underneath the phi GEMM
         // phi.1 + b + h (residual with the un-normalised h) -> h
         wait_D();
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
           float x[16], hr[16];
           load_D(cc, x);
-          load_rows(io, a.h, cc, hr);
+          take_rows(io, hr);
+          if (cc < 3) issue_rows(io, a.h, cc + 1);
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
             const float4 b = bias_at(1, cc, j4);
