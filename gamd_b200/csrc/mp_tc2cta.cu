@@ -908,7 +908,6 @@ int mp_edge_tc2_launch(gamd_ctx* ctx, int layer, cudaStream_t st, int which, boo
   // nsplit needs the N-split row order of the pair weight images (capi.cu builds them by ctx->mp_variant)
   if (ctx->mp_variant == 11) k_mp_edge_tc2<false, false, true, 0, true><<<grid, THREADS, smem, st>>>(a);
   else if (ctx->mp_variant == 12) k_mp_edge_tc2<false, false, true, 0, false, true><<<grid, THREADS, smem, st>>>(a);
-
   else if (ctx->mp_variant == 9) k_mp_edge_tc2<false, false, true, 1><<<grid, THREADS, smem, st>>>(a);
   else if (ctx->mp_variant == 10) k_mp_edge_tc2<false, false, true, 2><<<grid, THREADS, smem, st>>>(a);
   else if (ctx->mp_variant == 8) k_mp_edge_tc2<false, false, true><<<grid, THREADS, smem, st>>>(a);
