@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mp_edge_tc(MpTcArgs a) {
     }
   } else if (warp == MMA_WARP) {
     // ===================== MMA issue (one thread): an event loop over the two tiles in flight =====================
-    // (A single thread issues a tcgen05.mma only every ~120 cycles - tc_ubench.cu - so a 24-MMA stage costs ~2.9k
+    // (A single thread issues a tcgen05.mma only every ~120 cycles - profiles/probes/tc_ubench.cu - so a 24-MMA stage costs ~2.9k
     // cycles of issue.  Variants with one issuer per tile slot, two issuers per stage, or K steps issued as the
     // previous epilogue publishes 16-column chunks were all measured SLOWER: they let the two tiles fall into
     // lockstep on the MUFU pipe; two issuers per accumulator also lose run-to-run determinism.)

@@ -7,7 +7,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
-#include "tc_common.cuh"
+#include "../../gamd_b200/csrc/tc_common.cuh"
 
 using namespace tc;
 

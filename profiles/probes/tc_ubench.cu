@@ -3,11 +3,11 @@
 // MUFU work, warp 8 issues a train of 128x128x16 bf16 MMAs (A from TMEM or from shared memory).  Every role
 // reports its own clock64 span, so the cost of running them together can be compared with running them alone.
 // Development tool behind the numbers in DESIGN.md ("what shares what"); not part of the library.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tc_ubench tc_ubench.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tc_ubench profiles/probes/tc_ubench.cu   (from the repository root)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "tc_common.cuh"
+#include "../../gamd_b200/csrc/tc_common.cuh"
 
 using namespace tc;
 
