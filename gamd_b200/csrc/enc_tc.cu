@@ -483,7 +483,12 @@ __global__ void __launch_bounds__(THREADS3, 1) k_edge_encode_tc3(EncTcArgs a) {
     };
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
       const int tile = grp * NSLOT3 + g;
-      if (tile >= ntiles) continue;
+      if (tile >= ntiles) {
+        // absent slot of the tail group: under the fixed service order its last home block is written by the tail
+        // group's GEMMs - tell the MMA warp that the previous tile's LayerNorm has read it
+        if (STATIC) announce();
+        continue;
+      }
       const uint32_t nact = (uint32_t)min(NSLOT3, ntiles - grp * NSLOT3);
       const int e = tile * TILE + r;
       const bool valid = e < E;
@@ -679,6 +684,16 @@ __global__ void __launch_bounds__(THREADS3, 1) k_edge_encode_tc3(EncTcArgs a) {
     for (int i = 0; i < n_my_groups; i++) {
       const int grp = blockIdx.x + i * gridDim.x;
       const int nact = min(NSLOT3, ntiles - grp * NSLOT3);
+      // tail group: the blocks of the absent slots are written too - not before those slots have read their last rows
+#pragma unroll
+      for (int q = 1; q < NSLOT3; q++) {
+        if (q < nact) continue;
+        uint32_t spins = 0;
+        while (!__all_sync(0xffffffffu, mbar_test_wait(&sm.a_ready[q], (a_par_bits >> q) & 1u)))
+          if (++spins > (1u << 26)) __trap();
+        a_par_bits ^= 1u << q;
+        tc_fence_after();
+      }
 #pragma unroll 1
       for (int s = 0; s < 3; s++) {
         const uint32_t off = s == 0 ? OFF_ENC0 : (s == 1 ? OFF_ENC2 : OFF_ENC4);

@@ -488,7 +488,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
     uint32_t nstage = 0;     // GEMMs of my slot so far (the stamp of the block hand-over, STAMP kernels)
     for (int grp = cid; grp < ngroups; grp += ncl) {
       const int sslot = grp * NSLOT + g;
-      if (sslot >= nsuper) continue;
+      if (sslot >= nsuper) {
+        // absent slot of the tail group.  Under the fixed service order the tail group's GEMMs rotate through all four
+        // blocks, this slot's last home included: tell the leader that the previous tile's sums have left it
+        if (STATIC) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(a_bar);
+        }
+        continue;
+      }
       const uint32_t nact = (uint32_t)min(NSLOT, nsuper - grp * NSLOT);   // slots at work in this group (< NSLOT: tail)
       const int tile = next_tile;
       const bool dbg_on = dbg_rec && cid == 0 && lane == 0 && dbg_n + 14 <= 256;
@@ -678,6 +687,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_mp_edg
     for (int i = 0; i < n_my_groups; i++) {
       const int grp = cid + i * ncl;
       const int nact = min(NSLOT, nsuper - grp * NSLOT);
+      // tail group: the blocks of the absent slots are written too - not before those slots have read their last sums
+#pragma unroll
+      for (int q = 1; q < NSLOT; q++) {
+        if (q < nact) continue;
+        uint32_t spins = 0;
+        while (!__all_sync(0xffffffffu, mbar_test_wait(&sm.a_ready[q], (a_par_bits >> q) & 1u)))
+          if (++spins > (1u << 26)) __trap();
+        a_par_bits ^= 1u << q;
+        tc_fence_after();
+      }
 #pragma unroll 1
       for (int s = 0; s < 4; s++) {
         const uint32_t bhi = wbase + (uint32_t)(s * 2) * WPART;
