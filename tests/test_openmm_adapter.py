@@ -130,3 +130,64 @@ def test_reference_driver_loop_with_reporter(tmp_path, fixtures_dir):
     assert abs(float(rows[2][2]) - ke[99]) <= 1e-6 * ke[99]
     assert abs(float(rows[2][3]) - 2 * ke[99] / (3 * 258 * KB)) <= 1e-6 * float(rows[2][3])
     eng.close()
+
+
+def test_run_gnn_md_call_sequence_matches_the_reference_loop():
+    """the order of OpenMM calls of code/LJ/test_script/test_nosehoover.py:100-118, on recording stand-ins: integrator 0 is
+    current for the first half (thermostat state copied from the second integrator except on the first step, force in
+    ``force_last``), positions are read with ``enforcePeriodicBox`` in Angstrom for the model, integrator 1 for the
+    second half (state copied from the first, force in ``gnn_force``); the Langevin pair copies nothing."""
+    log = []
+
+    class Integ:
+        def __init__(self, name, nhc=True):
+            self.name = name
+            if nhc:
+                self.copy_state_from_integrator = lambda other: log.append((name, "copy_from", other.name))
+
+        def setPerDofVariableByName(self, var, f):
+            log.append((self.name, "set", var, float(np.asarray(f).sum())))
+
+    class Compound:
+        def setCurrentIntegrator(self, k):
+            log.append(("compound", "current", k))
+
+    class Ctx:
+        def __init__(self):
+            self.n = 0
+
+        def getState(self, getPositions=False, enforcePeriodicBox=False, **kw):
+            log.append(("context", "getState", bool(getPositions), bool(enforcePeriodicBox)))
+            self.n += 1
+            return _State(0.0, 0.0, x=np.full((2, 3), 0.1 * self.n))      # nm
+
+    class Sim:
+        def __init__(self):
+            self.context, self.currentStep = Ctx(), 0
+
+        def step(self, n):
+            self.currentStep += n
+            log.append(("simulation", "step", n))
+
+    def forces(pos_angstrom):
+        log.append(("model", "predict_forces", float(pos_angstrom[0, 0])))
+        return np.full((2, 3), pos_angstrom[0, 0])
+
+    i1, i2 = Integ("first"), Integ("second")
+    sim = Sim()
+    f = run_gnn_md(sim, Compound(), i1, i2, forces, 2)
+    want_step = lambda t, x_in, x_out: [                                     # noqa: E731
+        ("compound", "current", 0)] + ([("first", "copy_from", "second")] if t else []) + [
+        ("first", "set", "force_last", 6.0 * x_in), ("simulation", "step", 1),
+        ("context", "getState", True, True), ("model", "predict_forces", x_out),
+        ("compound", "current", 1), ("second", "copy_from", "first"), ("second", "set", "gnn_force", 6.0 * x_out),
+        ("simulation", "step", 1)]
+    expect = [("context", "getState", True, True), ("model", "predict_forces", 1.0)] + want_step(0, 1.0, 2.0) + want_step(1, 2.0, 3.0)
+    norm = lambda seq: [tuple(round(v, 9) if isinstance(v, float) else v for v in e) for e in seq]   # noqa: E731
+    assert norm(log) == norm(expect)
+    assert sim.currentStep == 4 and np.allclose(f, 3.0)
+    # Langevin / Andersen pairs (test_langevin.py:95-113): no thermostat state to copy, the first half reads 'gnn_force'
+    log.clear()
+    run_gnn_md(Sim(), Compound(), Integ("first", nhc=False), Integ("second", nhc=False), forces, 1, first_var="gnn_force",
+               force=np.zeros((2, 3)))
+    assert not any(e[1] == "copy_from" for e in log) and log[1] == ("first", "set", "gnn_force", 0.0)
